@@ -1,0 +1,273 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), split-fp16 operands.
+//
+// Replaces (reference, per image, fp32): im2col_gpu (src/caffe/util/im2col.cu:8-62) +
+// caffe_gpu_gemm/cublasSgemm (math_functions.cu:13-27) in
+// BaseConvolutionLayer::forward_gpu_gemm (base_conv_layer.cpp:325-341), plus the
+// BatchNorm/Scale/ReLU/Eltwise layers that follow it (batch_norm_layer.cu:10-90,
+// scale_layer.cu:30-56, relu_layer.cu:17-32, eltwise_layer.cu:47-53) as a fused epilogue.
+//
+// GEMM view: D[128 output pixels][BN out-channels] += A[pixels][64 ch of tap t] * W[BN][64],
+// looping over taps and 64-channel chunks.  Activations live in HBM as NHWC "split fp16":
+// plane 0 = hi = fp16(x), plane 1 = lo = fp16(x - hi); weights likewise.  Each K-step issues
+// three kind::f16 MMAs (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator: ~22 mantissa
+// bits per operand, fp32-level parity, at 1/3 of the f16 tensor rate.
+//
+// Pipeline (persistent CTAs, static round-robin tile schedule):
+//   warp 0   TMA producer: 4 bulk-tensor loads / stage (A_hi, A_lo: 5-D NHWC boxes with
+//            negative/OOB coordinates zero-filled = padding & dilation; B_hi, B_lo)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees stages
+//   warps 2-5 epilogue: tcgen05.ld accumulator -> *scale[c] + shift[c] (+ residual) (ReLU)
+//            -> split fp16 NHWC stores (or fp32 rows for the head GEMMs)
+//   TMEM holds two accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "dc_ptx.cuh"
+
+namespace dc {
+
+constexpr int kBM = 128;        // output pixels per tile (TMEM lanes)
+constexpr int kBK = 64;         // fp16 channels per K-chunk = one 128-byte swizzle row
+constexpr int kMaxTaps = 9;
+constexpr int kConvThreads = 192;
+
+enum OutMode : int { kOutSplitNHWC = 0, kOutF32Rows = 1 };
+
+struct ConvParams {
+  int H, W;                 // input spatial dims as seen by the A tensor map
+  int Ho, Wo, Cout;         // output geometry (Cout = real channel count)
+  int Cin;                  // multiple of 64
+  int ntaps;
+  int tap_dy[kMaxTaps];     // input row/col offset of each tap relative to the output pixel
+  int tap_dx[kMaxTaps];
+  int TH, TW;               // tile rectangle, TH * TW == 128
+  int tiles_x, tiles_y;     // per image
+  int n_tiles_m;            // N * tiles_y * tiles_x
+  int n_tiles_n;            // ceil(Cout / BN)
+  const float* scale;       // [n_tiles_n * BN] per-channel multiplier (folded BN*Scale*weight pow2)
+  const float* shift;       // [n_tiles_n * BN]
+  const __half* res;        // residual (split NHWC, same geometry as the output) or nullptr
+  long long res_plane;      // elements between the hi and lo planes of res
+  void* out;
+  long long out_plane;      // elements between hi and lo planes (split mode)
+  int ldc;                  // row stride in floats (fp32-rows mode)
+  int relu;
+  int out_mode;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kABytes = kBM * kBK * 2;          // one plane of A per stage
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : 2 * BN;   // two accumulators
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int kchunks = p.Cin / kBK;
+  const int ksteps = p.ntaps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        const int tx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int img = mt / p.tiles_y;
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int ix = x0 + p.tap_dx[t], iy = y0 + p.tap_dy[t];
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
+            tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
+            const int kcoord = (t * kchunks + kc) * kBK;
+            tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
+            tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + static_cast<uint32_t>(acc * BN);
+        uint32_t accum = 0;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_hi = umma_desc_k_sw128(sa);
+          const uint64_t a_lo = umma_desc_k_sw128(sa + Cfg::kABytes);
+          const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * Cfg::kABytes);
+          const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);   // 16 fp16 = 32 B along K
+            umma_f16(d, a_hi + adv, b_hi + adv, idesc, accum);
+            accum = 1;
+            umma_f16(d, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_f16(d, a_lo + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;          // pixel row of the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int oy = ty * p.TH + row / p.TW;
+      const int ox = tx * p.TW + row % p.TW;
+      const bool valid = (oy < p.Ho) && (ox < p.Wo);
+      const long long pix = (static_cast<long long>(img) * p.Ho + oy) * p.Wo + ox;
+      const int n0 = nt * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (p.out_mode == kOutSplitNHWC && n0 + c0 >= p.Cout) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = fmaf(__uint_as_float(r[j]), __ldg(p.scale + n0 + c0 + j), __ldg(p.shift + n0 + c0 + j));
+        if (p.out_mode == kOutSplitNHWC) {
+          const long long off = pix * p.Cout + n0 + c0;
+          if (valid) {
+            if (p.res != nullptr) {
+              const uint4* rh = reinterpret_cast<const uint4*>(p.res + off);
+              const uint4* rl = reinterpret_cast<const uint4*>(p.res + p.res_plane + off);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+                const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+                const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
+                  v[g * 8 + e * 2 + 0] += fh.x + fl.x;
+                  v[g * 8 + e * 2 + 1] += fh.y + fl.y;
+                }
+              }
+            }
+            __half* oh = reinterpret_cast<__half*>(p.out) + off;
+            __half* ol = oh + p.out_plane;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 h4, l4;
+              __half2* hh = reinterpret_cast<__half2*>(&h4);
+              __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = v[g * 8 + e * 2], b = v[g * 8 + e * 2 + 1];
+                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                __half ah, al, bh, bl;
+                split_f16(a, ah, al);
+                split_f16(b, bh, bl);
+                hh[e] = __halves2half2(ah, bh);
+                ll[e] = __halves2half2(al, bl);
+              }
+              reinterpret_cast<uint4*>(oh)[g] = h4;
+              reinterpret_cast<uint4*>(ol)[g] = l4;
+            }
+          }
+        } else {
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldc + n0 + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4 f = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+              o[g] = f;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace dc

@@ -1,0 +1,411 @@
+// extern "C" entry points of libdeepcut_b200.so (see include/deepcut_b200.h).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/deepcut_b200.h"
+#include "conv_igemm.cuh"
+#include "hbm_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define DC_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) return fail(DC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+bool g_inited = false;
+
+int ensure_init() {
+  if (g_inited) return DC_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(DC_ERR_NO_DEVICE, "no CUDA device: libdeepcut_b200 has no CPU path");
+  return dc_init(dev);
+}
+
+uint16_t f2h_bits(float f) {
+  // round-to-nearest-even fp32 -> fp16 bit pattern (host side, matches __float2half_rn)
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7FFFFFFFu;
+  if (x >= 0x7F800000u) return static_cast<uint16_t>(sign | 0x7C00u | ((x > 0x7F800000u) ? 0x200u : 0));
+  if (x >= 0x477FF000u) return static_cast<uint16_t>(sign | 0x7C00u);           // overflow -> inf
+  if (x < 0x33000001u) return static_cast<uint16_t>(sign);                        // underflow -> 0
+  int exp = static_cast<int>(x >> 23) - 127;
+  uint32_t man = (x & 0x7FFFFFu) | 0x800000u;
+  int shift;
+  uint32_t hexp;
+  if (exp < -14) { shift = 13 + (-14 - exp); hexp = 0; } else { shift = 13; hexp = static_cast<uint32_t>(exp + 15); }
+  uint32_t half_man = man >> shift;
+  const uint32_t rem = man & ((1u << shift) - 1u);
+  const uint32_t halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_man & 1u))) half_man++;
+  uint32_t out;
+  if (hexp == 0) out = half_man;                  // subnormal (may carry into exponent 1, which is correct)
+  else out = ((hexp - 1) << 10) + half_man;       // half_man includes the implicit bit (0x400)
+  return static_cast<uint16_t>(sign | out);
+}
+float h2f_bits(uint16_t h) {
+  const uint32_t sign = (h & 0x8000u) << 16;
+  uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, out;
+  if (exp == 0) {
+    if (man == 0) out = sign;
+    else {
+      int e = -1;
+      do { e++; man <<= 1; } while (!(man & 0x400u));
+      out = sign | static_cast<uint32_t>(127 - 15 - e) << 23 | ((man & 0x3FFu) << 13);
+    }
+  } else if (exp == 31) out = sign | 0x7F800000u | (man << 13);
+  else out = sign | ((exp + 112) << 23) | (man << 13);
+  float f;
+  memcpy(&f, &out, 4);
+  return f;
+}
+
+// Packs one logical GEMM row (K fp32 values gathered by `get`) as scaled split fp16.
+template <class Get>
+void pack_row(int K, Get get, uint16_t* hi, uint16_t* lo, float* rowscale) {
+  float mx = 0.f;
+  for (int k = 0; k < K; ++k) mx = fmaxf(mx, fabsf(get(k)));
+  float s = 1.f;
+  if (mx > 0.f && std::isfinite(mx)) {
+    int e;
+    frexpf(mx, &e);              // mx = m * 2^e, m in [0.5, 1)
+    s = ldexpf(1.f, 10 - e);     // mx * s in [2^9, 2^10)
+  }
+  for (int k = 0; k < K; ++k) {
+    const float v = get(k) * s;  // exact: power-of-two scaling
+    const uint16_t h = f2h_bits(v);
+    hi[k] = h;
+    lo[k] = f2h_bits(v - h2f_bits(h));
+  }
+  *rowscale = 1.f / s;
+}
+
+int tile_n_for(int cout) { return cout >= 256 ? 256 : (cout > 64 ? 128 : 64); }
+
+int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw, int th) {
+  const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, 2};
+  const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
+                                 (cuuint64_t)n * h * w * c * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)dc::kBK, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+  return DC_OK;
+}
+int encode_w_map(CUtensorMap* m, const void* base, int rows, long long K, int bn) {
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows * K * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)dc::kBK, (cuuint32_t)bn, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return DC_OK;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const dc::ConvParams& p, cudaStream_t st) {
+  const int tiles = p.n_tiles_m * p.n_tiles_n;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  dc::conv_igemm_kernel<BN><<<grid, dc::kConvThreads, dc::ConvCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int ew_grid(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(g_num_sms > 0 ? g_num_sms : 148) * 8;
+  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dc_version(void) { return 100; }
+const char* dc_last_error(void) { return g_err; }
+long long dc_launch_count(void) { return g_launches.load(); }
+
+int dc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ok++;
+  }
+  return ok;
+}
+
+int dc_init(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(DC_ERR_NO_DEVICE, "no CUDA device: libdeepcut_b200 has no CPU path");
+  }
+  DC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(DC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<256>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::kC1SmemFloats * 4));
+  g_inited = true;
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------ host-side transforms
+int dc_fold_bn_scale(const float* mean_sum, const float* var_sum, float factor, float eps, const float* gamma,
+                     const float* beta, int channels, float* a_out, float* b_out) {
+  if (!mean_sum || !var_sum || !a_out || !b_out || channels <= 0) return fail(DC_ERR_INVALID, "dc_fold_bn_scale: bad arguments");
+  const float sf = factor == 0.f ? 0.f : 1.f / factor;
+  for (int c = 0; c < channels; ++c) {
+    const float mean = mean_sum[c] * sf;
+    const float var = var_sum[c] * sf;
+    const double inv = 1.0 / std::sqrt(static_cast<double>(var) + static_cast<double>(eps));
+    const double g = gamma ? gamma[c] : 1.0;
+    const double b = beta ? beta[c] : 0.0;
+    a_out[c] = static_cast<float>(g * inv);
+    b_out[c] = static_cast<float>(b - static_cast<double>(mean) * g * inv);
+  }
+  return DC_OK;
+}
+
+int dc_tile_n(int cout) { return tile_n_for(cout); }
+int dc_packed_rows(int cout) {
+  const int bn = tile_n_for(cout);
+  return (cout + bn - 1) / bn * bn;
+}
+
+int dc_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, uint16_t* packed, float* rowscale) {
+  if (!w || !packed || !rowscale || cout <= 0 || cin <= 0 || kh <= 0 || kw <= 0) return fail(DC_ERR_INVALID, "dc_pack_conv_weight: bad arguments");
+  const int rows = dc_packed_rows(cout);
+  const long long K = static_cast<long long>(kh) * kw * cin;
+  uint16_t* hi = packed;
+  uint16_t* lo = packed + static_cast<long long>(rows) * K;
+  for (int r = 0; r < rows; ++r) {
+    if (r >= cout) {
+      memset(hi + r * K, 0, K * 2);
+      memset(lo + r * K, 0, K * 2);
+      rowscale[r] = 1.f;
+      continue;
+    }
+    const float* wr = w + static_cast<long long>(r) * cin * kh * kw;
+    const int taps = kh * kw;
+    pack_row(static_cast<int>(K), [&](int k) { const int t = k / cin, ci = k % cin; return wr[static_cast<long long>(ci) * taps + t]; },
+             hi + r * K, lo + r * K, rowscale + r);
+  }
+  return DC_OK;
+}
+
+int dc_pack_deconv_weight(const float* w, int cin, int cout, int kh, int kw, uint16_t* packed, float* rowscale) {
+  if (!w || !packed || !rowscale || cout <= 0 || cin <= 0 || kh <= 0 || kw <= 0) return fail(DC_ERR_INVALID, "dc_pack_deconv_weight: bad arguments");
+  const int taps = kh * kw;
+  const int nrows = cout * taps;
+  const int rows = dc_packed_rows(nrows);
+  const long long K = cin;
+  uint16_t* hi = packed;
+  uint16_t* lo = packed + static_cast<long long>(rows) * K;
+  for (int r = 0; r < rows; ++r) {
+    if (r >= nrows) {
+      memset(hi + r * K, 0, K * 2);
+      memset(lo + r * K, 0, K * 2);
+      rowscale[r] = 1.f;
+      continue;
+    }
+    // W[ci][co][p][q]; row r = co*taps + t  ->  element offset ci*cout*taps + r
+    pack_row(static_cast<int>(K), [&](int ci) { return w[static_cast<long long>(ci) * cout * taps + r]; }, hi + r * K,
+             lo + r * K, rowscale + r);
+  }
+  return DC_OK;
+}
+
+int dc_pack_conv1_weight(const float* w, float* packed) {
+  if (!w || !packed) return fail(DC_ERR_INVALID, "dc_pack_conv1_weight: bad arguments");
+  for (int co = 0; co < 64; ++co)
+    for (int k = 0; k < 147; ++k) packed[k * 64 + co] = w[co * 147 + k];
+  return DC_OK;
+}
+
+int dc_pool_out_size(int size, int kernel, int stride) {
+  // PoolingLayer::Reshape, pooling_layer.cpp:90-93 (pad 0): ceil((size - k) / s) + 1
+  return static_cast<int>(std::ceil(static_cast<float>(size - kernel) / stride)) + 1;
+}
+
+// ------------------------------------------------------------------ fused convolution
+int dc_conv_forward(const dc_conv_args* a, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!a || !a->x || !a->w_packed || !a->scale || !a->shift || !a->out) return fail(DC_ERR_INVALID, "dc_conv_forward: null argument");
+  if (a->cin % dc::kBK != 0) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: cin=%d is not a multiple of 64", a->cin);
+  if (a->kh * a->kw > dc::kMaxTaps) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: %dx%d filter exceeds 9 taps", a->kh, a->kw);
+  if (!a->out_f32_rows && a->cout % 32 != 0) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: cout=%d must be a multiple of 32 for split output", a->cout);
+  const int ho = a->h + 2 * a->pad - (a->dilation * (a->kh - 1) + 1) + 1;
+  const int wo = a->w + 2 * a->pad - (a->dilation * (a->kw - 1) + 1) + 1;
+  if (ho <= 0 || wo <= 0) return fail(DC_ERR_INVALID, "dc_conv_forward: empty output");
+  const int bn = tile_n_for(a->cout);
+  const int rows = dc_packed_rows(a->cout);
+  if (a->out_f32_rows && a->ldc < rows) return fail(DC_ERR_INVALID, "dc_conv_forward: ldc=%d < packed rows %d", a->ldc, rows);
+
+  dc::ConvParams p;
+  memset(&p, 0, sizeof(p));
+  int n = a->n, h = a->h, w = a->w;
+  const bool pointwise = (a->kh == 1 && a->kw == 1 && a->pad == 0);
+  int out_h = ho, out_w = wo;
+  if (pointwise) {   // a 1x1 conv is a plain GEMM over all pixels: flatten so tiles never straddle rows
+    w = n * h * w; h = 1; n = 1;
+    out_h = 1; out_w = w;
+  }
+  p.H = h; p.W = w; p.Ho = out_h; p.Wo = out_w; p.Cout = a->cout; p.Cin = a->cin;
+  p.ntaps = a->kh * a->kw;
+  for (int pp = 0; pp < a->kh; ++pp)
+    for (int q = 0; q < a->kw; ++q) {
+      p.tap_dy[pp * a->kw + q] = -a->pad + pp * a->dilation;
+      p.tap_dx[pp * a->kw + q] = -a->pad + q * a->dilation;
+    }
+  // tile rectangle with the least padded area
+  const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
+  long long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cand[i][0], th = cand[i][1];
+    const long long area = static_cast<long long>((out_w + tw - 1) / tw) * tw * ((out_h + th - 1) / th) * th;
+    if (best < 0 || area < best) { best = area; p.TW = tw; p.TH = th; }
+  }
+  p.tiles_x = (out_w + p.TW - 1) / p.TW;
+  p.tiles_y = (out_h + p.TH - 1) / p.TH;
+  p.n_tiles_m = n * p.tiles_x * p.tiles_y;
+  p.n_tiles_n = rows / bn;
+  p.scale = a->scale; p.shift = a->shift;
+  p.res = static_cast<const __half*>(a->residual);
+  const long long out_elems = static_cast<long long>(a->n) * ho * wo * a->cout;
+  p.res_plane = out_elems;
+  p.out = a->out;
+  p.out_plane = out_elems;
+  p.ldc = a->ldc;
+  p.relu = a->relu;
+  p.out_mode = a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC;
+
+  CUtensorMap ta, tb;
+  if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH)) return rc;
+  if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, bn)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_conv<256>(ta, tb, p, st);
+    case 128: return launch_conv<128>(ta, tb, p, st);
+    default: return launch_conv<64>(ta, tb, p, st);
+  }
+}
+
+// ------------------------------------------------------------------ HBM kernels
+int dc_conv1_forward(const float* x, int n, int h, int w, const float* w147x64, const float* scale,
+                     const float* shift, void* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!x || !w147x64 || !scale || !shift || !out) return fail(DC_ERR_INVALID, "dc_conv1_forward: null argument");
+  const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+  const int tiles = n * ((ho + dc::kC1TileH - 1) / dc::kC1TileH) * ((wo + dc::kC1TileW - 1) / dc::kC1TileW);
+  dc::conv1_7x7s2_kernel<<<tiles, 256, dc::kC1SmemFloats * 4, static_cast<cudaStream_t>(stream)>>>(
+      x, w147x64, scale, shift, static_cast<__half*>(out), static_cast<long long>(n) * ho * wo * 64, n, h, w, ho, wo);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int dc_maxpool_forward(const void* x, int n, int h, int w, int c, int kernel, int stride, void* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!x || !out || c % 8 != 0) return fail(DC_ERR_INVALID, "dc_maxpool_forward: bad arguments (c must be a multiple of 8)");
+  const int ho = dc_pool_out_size(h, kernel, stride), wo = dc_pool_out_size(w, kernel, stride);
+  const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
+  dc::maxpool_split_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<long long>(n) * h * w * c, static_cast<__half*>(out),
+      static_cast<long long>(n) * ho * wo * c, n, h, w, c, ho, wo, kernel, stride);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int dc_subsample_forward(const void* x, int n, int h, int w, int c, int stride, void* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!x || !out || c % 8 != 0 || stride < 1) return fail(DC_ERR_INVALID, "dc_subsample_forward: bad arguments");
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+  const long long total = static_cast<long long>(n) * ho * wo * (c / 8) * 2;
+  dc::subsample_split_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<long long>(n) * h * w * c, static_cast<__half*>(out),
+      static_cast<long long>(n) * ho * wo * c, n, h, w, c, ho, wo, stride);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int dc_head_finish(const float* col, int ldcol, int col_off, const float* skip, int ldskip, int skip_off,
+                   float* out, int n, int cout, int h, int w, int ho, int wo, int sigmoid, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!col || !skip || !out) return fail(DC_ERR_INVALID, "dc_head_finish: null argument");
+  const long long total = static_cast<long long>(n) * cout * ho * wo;
+  dc::head_finish_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      col, ldcol, col_off, skip, ldskip, skip_off, out, n, cout, h, w, ho, wo, sigmoid);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!x || !out) return fail(DC_ERR_INVALID, "dc_nchw_to_split: null argument");
+  const long long total = static_cast<long long>(n) * c * h * w;
+  dc::nchw_to_split_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__half*>(out), total, n, c, h, w);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int dc_split_to_nchw(const void* x, int n, int c, int h, int w, float* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!x || !out) return fail(DC_ERR_INVALID, "dc_split_to_nchw: null argument");
+  const long long total = static_cast<long long>(n) * c * h * w;
+  dc::split_to_nchw_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), total, out, n, c, h, w);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+}  // extern "C"

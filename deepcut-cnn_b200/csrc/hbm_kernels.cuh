@@ -1,0 +1,252 @@
+// HBM-bound kernels of the DeeperCut forward path (sm_100a): stem convolution, max-pool,
+// stride-2 subsample, head finish (col2im + crop + add + sigmoid) and layout converters.
+// All activations between kernels are NHWC "split fp16" (plane 0 = hi, plane 1 = lo).
+#pragma once
+#include "dc_ptx.cuh"
+
+namespace dc {
+
+// ---------------------------------------------------------------------------------------
+// conv1: 7x7 / stride 2 / pad 3, 3 -> 64 channels, fp32 NCHW in (the `data` blob as Caffe
+// holds it), fused BatchNorm+Scale+ReLU, split-fp16 NHWC out.
+// Replaces ConvolutionLayer::Forward_gpu (conv_layer.cu:8-24: im2col K=147 + SGEMM M=64) +
+// bn_conv1/scale_conv1/conv1_relu.  K=147 is too ragged for a TMA/UMMA tile and the layer is
+// 0.8 % of the net's FLOPs, so this is an fp32 FFMA direct convolution: a CTA stages the
+// input patch of an 8x32 output tile and the whole 147x64 filter bank in shared memory; each
+// thread owns one output pixel x 64 channels (weights are warp-broadcast LDS.128).
+// ---------------------------------------------------------------------------------------
+constexpr int kC1TileH = 8, kC1TileW = 32, kC1K = 7, kC1Cout = 64;
+constexpr int kC1PatchH = kC1TileH * 2 + 5, kC1PatchW = kC1TileW * 2 + 5;   // 21 x 69
+constexpr int kC1PatchWPad = kC1PatchW + 2;                                 // 71: odd stride, no 2-way conflicts
+constexpr int kC1SmemFloats = 147 * 64 + 3 * kC1PatchH * kC1PatchWPad;
+
+__global__ void __launch_bounds__(256) conv1_7x7s2_kernel(const float* __restrict__ x, const float* __restrict__ wk,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, __half* __restrict__ out,
+                                                          long long out_plane, int N, int H, int W, int Ho, int Wo) {
+  extern __shared__ float c1s[];
+  float* sw = c1s;                    // [147][64]  (k = (ci*7+p)*7+q, co)
+  float* sp = c1s + 147 * 64;         // [3][21][71]
+  const int tiles_x = (Wo + kC1TileW - 1) / kC1TileW;
+  const int tiles_y = (Ho + kC1TileH - 1) / kC1TileH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int n = t / tiles_y;
+  const int oy0 = ty * kC1TileH, ox0 = tx * kC1TileW;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+
+  for (int i = threadIdx.x; i < 147 * 64 / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wk) + i);
+  for (int i = threadIdx.x; i < 3 * kC1PatchH * kC1PatchW; i += blockDim.x) {
+    const int c = i / (kC1PatchH * kC1PatchW);
+    const int r = (i / kC1PatchW) % kC1PatchH;
+    const int col = i % kC1PatchW;
+    const int iy = iy0 + r, ix = ix0 + col;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<long long>(n) * 3 + c) * H + iy) * W + ix);
+    sp[(c * kC1PatchH + r) * kC1PatchWPad + col] = v;
+  }
+  __syncthreads();
+
+  const int ly = threadIdx.x / kC1TileW, lx = threadIdx.x % kC1TileW;
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    for (int p = 0; p < 7; ++p) {
+      const float* prow = sp + (c * kC1PatchH + ly * 2 + p) * kC1PatchWPad + lx * 2;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const float xv = prow[q];
+        const float4* w4 = reinterpret_cast<const float4*>(sw + ((c * 7 + p) * 7 + q) * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 wv = w4[j];
+          acc[4 * j + 0] = fmaf(xv, wv.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(xv, wv.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(xv, wv.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(xv, wv.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  if (oy < Ho && ox < Wo) {
+    const long long off = ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * 64;
+    __half* oh = out + off;
+    __half* ol = out + out_plane + off;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 h4, l4;
+      __half2* hh = reinterpret_cast<__half2*>(&h4);
+      __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c0 = g * 8 + e * 2;
+        float a = fmaxf(fmaf(acc[c0], __ldg(scale + c0), __ldg(shift + c0)), 0.f);
+        float b = fmaxf(fmaf(acc[c0 + 1], __ldg(scale + c0 + 1), __ldg(shift + c0 + 1)), 0.f);
+        __half ah, al, bh, bl;
+        split_f16(a, ah, al);
+        split_f16(b, bh, bl);
+        hh[e] = __halves2half2(ah, bh);
+        ll[e] = __halves2half2(al, bl);
+      }
+      reinterpret_cast<uint4*>(oh)[g] = h4;
+      reinterpret_cast<uint4*>(ol)[g] = l4;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// MAX pooling k x k / stride s, pad 0, Caffe ceil-mode output size, windows clipped at the
+// bottom/right edge (PoolingLayer::Forward_gpu pooling_layer.cu:10-47).  One thread = one
+// output pixel x 8 channels (128-bit loads of hi and lo).  The winner's (hi, lo) pair is
+// copied verbatim, so the result is bit-identical to pooling the joined values.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_split_kernel(const __half* __restrict__ in, long long in_plane,
+                                                            __half* __restrict__ out, long long out_plane, int N,
+                                                            int H, int W, int C, int Ho, int Wo, int k, int s) {
+  const int cg = C / 8;
+  const long long total = static_cast<long long>(N) * Ho * Wo * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    long long pidx = i / cg;
+    const int ox = static_cast<int>(pidx % Wo);
+    pidx /= Wo;
+    const int oy = static_cast<int>(pidx % Ho);
+    const int n = static_cast<int>(pidx / Ho);
+    const int y0 = oy * s, x0 = ox * s;
+    const int y1 = min(y0 + k, H), x1 = min(x0 + k, W);
+    float best[8];
+    __half bh[8], bl[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -3.402823466e+38f; bh[e] = __float2half(0.f); bl[e] = __float2half(0.f); }
+    for (int y = y0; y < y1; ++y)
+      for (int xx = x0; xx < x1; ++xx) {
+        const long long off = ((static_cast<long long>(n) * H + y) * W + xx) * C + g * 8;
+        const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(in + off));
+        const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(in + in_plane + off));
+        const __half* hh = reinterpret_cast<const __half*>(&h4);
+        const __half* ll = reinterpret_cast<const __half*>(&l4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float v = join_f16(hh[e], ll[e]);
+          if (v > best[e]) { best[e] = v; bh[e] = hh[e]; bl[e] = ll[e]; }
+        }
+      }
+    const long long ooff = ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + g * 8;
+    *reinterpret_cast<uint4*>(out + ooff) = *reinterpret_cast<const uint4*>(bh);
+    *reinterpret_cast<uint4*>(out + out_plane + ooff) = *reinterpret_cast<const uint4*>(bl);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Stride-s spatial subsample (both planes): out[n,y,x,:] = in[n,s*y,s*x,:].  Feeds the four
+// stride-2 1x1 convolutions (res3a/res4a branch1 + branch2a), which the reference runs through
+// im2col because stride != 1 (base_conv_layer.cpp:109-116).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) subsample_split_kernel(const __half* __restrict__ in, long long in_plane,
+                                                              __half* __restrict__ out, long long out_plane, int N,
+                                                              int H, int W, int C, int Ho, int Wo, int s) {
+  const int cg = C / 8;
+  const long long total = static_cast<long long>(N) * Ho * Wo * cg * 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    long long pidx = i / cg;
+    const int ox = static_cast<int>(pidx % Wo);
+    pidx /= Wo;
+    const int oy = static_cast<int>(pidx % Ho);
+    pidx /= Ho;
+    const int n = static_cast<int>(pidx % N);
+    const int plane = static_cast<int>(pidx / N);
+    const long long src = plane * in_plane + ((static_cast<long long>(n) * H + oy * s) * W + ox * s) * C + g * 8;
+    const long long dst = plane * out_plane + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + g * 8;
+    *reinterpret_cast<uint4*>(out + dst) = __ldg(reinterpret_cast<const uint4*>(in + src));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Head finish.  Inputs are the two fp32 GEMM results of the merged heads:
+//   col  [N*h*w][ldcol]  col(pixel(i,j), co*9 + p*3 + q) = sum_ci res5c[ci,i,j] * Wd[ci,co,p,q]
+//   skip [N*Ho*Wo][ldskip] = 1x1 heads on res3b7 (+ both biases, folded into the GEMM shift)
+// Output (fp32 NCHW, the layout Caffe exposes):  out[n,co,y,x] =
+//   skip + sum_{p,q : (y-p),(x-q) even, in range} col(((y-p)/2,(x-q)/2), co,p,q)  [-> sigmoid]
+// i.e. DeconvolutionLayer col2im (im2col.cu:246-305) + Crop to Ho x Wo at offset 0
+// (crop_layer.cu:9-38) + Eltwise SUM (eltwise_layer.cu:47-53) + Sigmoid (sigmoid_layer.cu:8-24).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ col, int ldcol, int col_off,
+                                                          const float* __restrict__ skip, int ldskip, int skip_off,
+                                                          float* __restrict__ out, int N, int Cout, int h, int w,
+                                                          int Ho, int Wo, int do_sigmoid) {
+  const long long total = static_cast<long long>(N) * Cout * Ho * Wo;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % Wo);
+    long long r = i / Wo;
+    const int y = static_cast<int>(r % Ho);
+    r /= Ho;
+    const int co = static_cast<int>(r % Cout);
+    const int n = static_cast<int>(r / Cout);
+    float up = 0.f;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const int yy = y - p;
+      if (yy < 0 || (yy & 1) || (yy >> 1) >= h) continue;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int xx = x - q;
+        if (xx < 0 || (xx & 1) || (xx >> 1) >= w) continue;
+        const long long pix = (static_cast<long long>(n) * h + (yy >> 1)) * w + (xx >> 1);
+        up += __ldg(col + pix * ldcol + col_off + co * 9 + p * 3 + q);
+      }
+    }
+    const long long opix = (static_cast<long long>(n) * Ho + y) * Wo + x;
+    float v = __ldg(skip + opix * ldskip + skip_off + co) + up;
+    if (do_sigmoid) v = 1.f / (1.f + expf(-v));
+    out[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Layout converters (blob materialisation / test harness): fp32 NCHW <-> split-fp16 NHWC.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ in, __half* __restrict__ out,
+                                                            long long out_plane, int N, int C, int H, int W) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long r = i / C;
+    const int x = static_cast<int>(r % W);
+    r /= W;
+    const int y = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    const float v = __ldg(in + ((static_cast<long long>(n) * C + c) * H + y) * W + x);
+    __half hi, lo;
+    split_f16(v, hi, lo);
+    out[i] = hi;
+    out[out_plane + i] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) split_to_nchw_kernel(const __half* __restrict__ in, long long in_plane,
+                                                            float* __restrict__ out, int N, int C, int H, int W) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    long long r = i / W;
+    const int y = static_cast<int>(r % H);
+    r /= H;
+    const int c = static_cast<int>(r % C);
+    const int n = static_cast<int>(r / C);
+    const long long src = ((static_cast<long long>(n) * H + y) * W + x) * C + c;
+    out[i] = join_f16(in[src], in[in_plane + src]);
+  }
+}
+
+}  // namespace dc

@@ -1,0 +1,66 @@
+"""ctypes binding of include/deepcut_b200.h.  Fails loudly if the CUDA library is missing:
+there is no CPU fallback for the hot path."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdeepcut_b200.so")
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int),
+                ("cout", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("pad", C.c_int), ("dilation", C.c_int),
+                ("w_packed", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
+                ("relu", C.c_int), ("out_f32_rows", C.c_int), ("ldc", C.c_int), ("out", C.c_void_p)]
+
+
+_SIGS = {
+    "dc_version": (C.c_int, []),
+    "dc_last_error": (C.c_char_p, []),
+    "dc_device_count": (C.c_int, []),
+    "dc_init": (C.c_int, [C.c_int]),
+    "dc_launch_count": (C.c_longlong, []),
+    "dc_fold_bn_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p]),
+    "dc_packed_rows": (C.c_int, [C.c_int]),
+    "dc_tile_n": (C.c_int, [C.c_int]),
+    "dc_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dc_pack_deconv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dc_pack_conv1_weight": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dc_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "dc_conv1_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "dc_maxpool_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p]),
+    "dc_pool_out_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "dc_subsample_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "dc_head_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dc_nchw_to_split": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dc_split_to_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run __graft_entry__.build() (the hot path has no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(_lib, name)      # AttributeError = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libdeepcut_b200: rc=%d: %s" % (rc, lib().dc_last_error().decode()))

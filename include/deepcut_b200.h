@@ -1,0 +1,116 @@
+/* deepcut_b200.h -- C ABI of the B200-native DeeperCut forward kernels.
+ *
+ * This is the seam between the kept C++ Caffe host (Net/Layer/Blob, caffe_host/) and the
+ * hand-written sm_100a CUDA.  The reference has no C ABI; each entry point names the
+ * reference interface (file:line under /root/reference) whose GPU work it replaces.
+ *
+ * Conventions: plain C types only; device pointers are caller-owned; `stream` is a
+ * cudaStream_t passed as void*; every function returns 0 on success and a non-zero code on
+ * failure with a message available from dc_last_error() (never aborts -- the C++ Forward_gpu
+ * wrappers turn non-zero into CHECK failures, matching the reference's glog convention,
+ * include/caffe/util/device_alternate.hpp:48-66).  There is no CPU fallback: compute entry
+ * points fail with DC_ERR_NO_DEVICE when no sm_100 GPU is present.
+ *
+ * Activation layout between kernels ("split NHWC"): fp16 [2][N][H][W][C]; plane 0 = hi =
+ * fp16(x), plane 1 = lo = fp16(x - hi).  Blob-facing tensors are fp32 NCHW as in
+ * include/caffe/blob.hpp:153-164.
+ */
+#ifndef DEEPCUT_B200_H_
+#define DEEPCUT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_OK 0
+#define DC_ERR_INVALID 1
+#define DC_ERR_CUDA 2
+#define DC_ERR_NO_DEVICE 3
+#define DC_ERR_UNSUPPORTED 4
+
+/* ---- library ---------------------------------------------------------------------- */
+int dc_version(void);
+const char* dc_last_error(void);
+/* Number of usable sm_100 devices (0 on a CPU-only host; never fails). */
+int dc_device_count(void);
+/* Binds the calling thread to `device`, resolves the driver's tensor-map encoder, raises the
+ * kernels' dynamic shared-memory limits.  Replaces Caffe::SetDevice (src/caffe/common.cpp:140-158). */
+int dc_init(int device);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+long long dc_launch_count(void);
+
+/* ---- load-time weight transforms (host side, no GPU needed) ------------------------- */
+/* y = (x - mean*sf) / sqrt(var*sf + eps) * gamma + beta  ==  a*x + b with sf = (factor==0 ? 0 : 1/factor)
+ * BatchNormLayer inference branch (src/caffe/layers/batch_norm_layer.cpp:86-93,137-149) folded with
+ * ScaleLayer (+bias) (scale_layer.cpp:120-133, bias_layer.cpp:72-88).  gamma/beta may be NULL (=1/0). */
+int dc_fold_bn_scale(const float* mean_sum, const float* var_sum, float factor, float eps, const float* gamma,
+                     const float* beta, int channels, float* a_out, float* b_out);
+
+/* Rows of the packed weight matrix after padding Cout to the conv kernel's N tile. */
+int dc_packed_rows(int cout);
+/* N tile (out-channels per CTA tile) the conv kernel uses for `cout` output channels. */
+int dc_tile_n(int cout);
+/* Packs a Caffe Convolution weight blob W[cout][cin][kh][kw] (base_conv_layer.cpp:135-140) into the
+ * K-major split-fp16 matrix the implicit GEMM reads: packed[2][rows][K], K = (p*kw+q)*cin + ci,
+ * rows = dc_packed_rows(cout) (zero padded).  Each row is multiplied by a power of two so its
+ * largest |w| lands in [2^9, 2^10) (keeps the lo plane out of fp16 subnormals); rowscale[r]
+ * receives the exact inverse (0 for padding rows... 1 is stored so products stay finite). */
+int dc_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, uint16_t* packed, float* rowscale);
+/* Same for a Deconvolution blob W[cin][cout][kh][kw] (reverse_dimensions, base_conv_layer.cpp:125-131):
+ * GEMM row = co*kh*kw + p*kw + q, K = ci; rows = dc_packed_rows(cout*kh*kw). */
+int dc_pack_deconv_weight(const float* w, int cin, int cout, int kh, int kw, uint16_t* packed, float* rowscale);
+/* conv1 filter bank W[64][3][7][7] -> fp32 [147][64] (k = (ci*7+p)*7+q major, co minor). */
+int dc_pack_conv1_weight(const float* w, float* packed);
+
+/* ---- fused convolution (tcgen05 implicit GEMM) ------------------------------------- */
+typedef struct dc_conv_args {
+  /* input: split NHWC [2][n][h][w][cin], cin % 64 == 0 */
+  const void* x;
+  int n, h, w, cin;
+  /* filter geometry; stride must be 1 (stride-2 1x1 convs go through dc_subsample first) */
+  int cout, kh, kw, pad, dilation;
+  const void* w_packed;      /* device copy of dc_pack_*_weight output, rows = dc_packed_rows(cout) */
+  const float* scale;        /* device [dc_packed_rows(cout)]: folded a[c] * rowscale[c] */
+  const float* shift;        /* device [dc_packed_rows(cout)]: folded b[c] (or bias) */
+  const void* residual;      /* split NHWC, output geometry, or NULL (Eltwise SUM shortcut) */
+  int relu;
+  int out_f32_rows;          /* 0: split NHWC out [2][n][ho][wo][cout]; 1: fp32 rows out[pixel][ldc] */
+  int ldc;                   /* fp32-rows mode: row stride in floats, >= dc_packed_rows(cout) */
+  void* out;
+} dc_conv_args;
+/* Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-24) =
+ * im2col_gpu (util/im2col.cu:8-62) + cublasSgemm (util/math_functions.cu:13-27) per image, and the
+ * following BatchNormLayer/ScaleLayer/ReLULayer/EltwiseLayer::Forward_gpu passes
+ * (batch_norm_layer.cu:10-90, scale_layer.cu:30-56, relu_layer.cu:17-32, eltwise_layer.cu:47-53).
+ * Also serves DeconvolutionLayer's GEMM (base_conv_layer.cpp:351-367) with kh=kw=1 and a
+ * dc_pack_deconv_weight matrix (out_f32_rows = 1). */
+int dc_conv_forward(const dc_conv_args* args, void* stream);
+
+/* ---- HBM-bound kernels --------------------------------------------------------------- */
+/* conv1 7x7/2 pad 3 (3->64) + folded BN/Scale + ReLU.  x: fp32 NCHW [n][3][h][w] (the `data` blob);
+ * w147x64: device dc_pack_conv1_weight output; out: split NHWC [2][n][ho][wo][64].
+ * Replaces conv_layer.cu:8-24 (K=147 im2col+SGEMM) + bn/scale/relu for layer conv1. */
+int dc_conv1_forward(const float* x, int n, int h, int w, const float* w147x64, const float* scale,
+                     const float* shift, void* out, void* stream);
+/* MAX pool, pad 0, ceil-mode (PoolingLayer::Forward_gpu, pooling_layer.cu:10-47,158-180). */
+int dc_maxpool_forward(const void* x, int n, int h, int w, int c, int kernel, int stride, void* out, void* stream);
+int dc_pool_out_size(int size, int kernel, int stride);
+/* out[n,y,x,:] = x[n,s*y,s*x,:] (what im2col does for a strided 1x1 conv, im2col.cu:8-39). */
+int dc_subsample_forward(const void* x, int n, int h, int w, int c, int stride, void* out, void* stream);
+/* Head finish: col2im of the 3x3/2 deconvolution (im2col.cu:246-305) + Crop to (ho,wo) at offset 0
+ * (crop_layer.cu:9-38) + Eltwise SUM with the 1x1 skip head (eltwise_layer.cu:47-53) [+ Sigmoid,
+ * sigmoid_layer.cu:8-24].  col: fp32 [n*h*w][ldcol], column col_off + co*9 + p*3 + q;
+ * skip: fp32 [n*ho*wo][ldskip], column skip_off + co; out: fp32 NCHW [n][cout][ho][wo]. */
+int dc_head_finish(const float* col, int ldcol, int col_off, const float* skip, int ldskip, int skip_off,
+                   float* out, int n, int cout, int h, int w, int ho, int wo, int sigmoid, void* stream);
+/* Blob materialisation: fp32 NCHW <-> split NHWC. */
+int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream);
+int dc_split_to_nchw(const void* x, int n, int c, int h, int w, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPCUT_B200_H_ */

@@ -1,0 +1,52 @@
+"""GPU-side harness for the kernel parity tests: runs single layers through the C ABI with torch
+holding device memory (torch = plumbing only)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+import dcutil
+from dcutil import libdc, ptr
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def init():
+    libdc.check(libdc.lib().dc_init(torch.cuda.current_device()))
+
+
+def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_rows=False):
+    """Runs dc_conv_forward on fp32 NCHW numpy inputs; returns fp32 NCHW numpy (or fp32 rows)."""
+    L = libdc.lib()
+    n, ci, h, wd = x_nchw.shape
+    co, _, kh, kw = w.shape
+    packed, rs = dcutil.pack_conv(w)
+    rows = packed.shape[1]
+    scale = np.ones(rows, np.float32)
+    shift = np.zeros(rows, np.float32)
+    scale[:co] = a * rs[:co]
+    shift[:co] = b
+    ho = h + 2 * pad - (dil * (kh - 1) + 1) + 1
+    wo = wd + 2 * pad - (dil * (kw - 1) + 1) + 1
+    xs = dev(dcutil.np_split(x_nchw))
+    wp, sc, sh = dev(packed), dev(scale), dev(shift)
+    res = dev(dcutil.np_split(residual_nchw)) if residual_nchw is not None else None
+    if f32_rows:
+        out = torch.full((n * ho * wo, rows), float("nan"), dtype=torch.float32, device="cuda")
+    else:
+        out = torch.full((2, n, ho, wo, co), float("nan"), dtype=torch.float16, device="cuda")
+    args = libdc.ConvArgs(x=xs.data_ptr(), n=n, h=h, w=wd, cin=ci, cout=co, kh=kh, kw=kw, pad=pad, dilation=dil,
+                          w_packed=wp.data_ptr(), scale=sc.data_ptr(), shift=sh.data_ptr(),
+                          residual=res.data_ptr() if res is not None else None, relu=int(relu),
+                          out_f32_rows=int(f32_rows), ldc=rows, out=out.data_ptr())
+    libdc.check(L.dc_conv_forward(C.byref(args), stream_ptr()))
+    torch.cuda.synchronize()
+    if f32_rows:
+        return out.cpu().numpy()
+    return dcutil.np_join(out.cpu().numpy())

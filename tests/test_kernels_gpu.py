@@ -1,0 +1,220 @@
+"""Kernel parity (GPU): every CUDA kernel through the C ABI vs the CPU oracle on seeded inputs.
+Tolerances: the reference's own layer tests use 1e-4 abs on O(1) data
+(src/caffe/test/test_convolution_layer.cpp:256); integer/copy kernels are bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import dcutil
+from dcutil import libdc
+from oracle import caffe_ref
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gpuharness
+    gpuharness.init()
+    return gpuharness
+
+
+def _bn_params(rng, c):
+    return (rng.uniform(0.5, 1.5, c).astype(np.float32), rng.normal(0, 0.3, c).astype(np.float32))
+
+
+# (cin, cout, k, pad, dil, H, W, N): one per distinct stride-1 backbone shape class of SURVEY 8(a'),
+# at spatial sizes with ragged tile edges (43x43 is the prototxt's own res5 size at 688x688).
+CONV_CASES = [
+    (64, 64, 1, 0, 1, 19, 23, 2),
+    (64, 64, 3, 1, 1, 19, 23, 2),
+    (64, 256, 1, 0, 1, 16, 16, 1),
+    (256, 64, 1, 0, 1, 9, 31, 2),
+    (128, 128, 3, 1, 1, 33, 17, 1),
+    (256, 256, 3, 1, 1, 16, 16, 2),
+    (1024, 256, 1, 0, 1, 8, 13, 1),
+    (256, 1024, 1, 0, 1, 8, 13, 2),
+    (512, 512, 3, 2, 2, 43, 43, 1),       # res5 dilated conv (test_convolution_layer.cpp:267 analogue)
+    (512, 2048, 1, 0, 1, 11, 9, 1),
+    (2048, 512, 1, 0, 1, 11, 9, 1),
+    (64, 64, 3, 3, 3, 21, 18, 1),         # dilation 3 (test_im2col_kernel.cu:55-58 fixture)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_bn_relu_matches_oracle(case, _gpu):
+    ci, co, k, pad, dil, h, w, n = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    x *= (rng.random((n, ci, h, w)) > 0.3)            # post-ReLU-like sparsity
+    wt = (rng.standard_normal((co, ci, k, k)) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32)
+    a, b = _bn_params(rng, co)
+    ref = caffe_ref.convolution(x, wt, None, 1, pad, dil)
+    ref = np.maximum(ref * a.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1), 0)
+    got = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True)
+    assert got.shape == ref.shape
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() < 1e-4, np.abs(got - ref).max()
+
+
+def test_conv_residual_add_relu(_gpu):
+    rng = np.random.default_rng(7)
+    n, ci, co, h, w = 2, 256, 1024, 12, 10
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, 1, 1)) * np.sqrt(2.0 / ci)).astype(np.float32)
+    a, b = _bn_params(rng, co)
+    shortcut = rng.standard_normal((n, co, h, w)).astype(np.float32)
+    branch = caffe_ref.convolution(x, wt, None, 1, 0, 1) * a.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1)
+    ref = caffe_ref.relu(caffe_ref.eltwise_sum([shortcut, branch.astype(np.float32)]))
+    got = _gpu.conv_bn(x, wt, a, b, relu=True, residual_nchw=shortcut)
+    assert np.abs(got - ref).max() < 1e-4
+    # no-ReLU / no-residual variant (projection shortcut branch1: conv + BN + Scale only)
+    got2 = _gpu.conv_bn(x, wt, a, b, relu=False)
+    assert np.abs(got2 - branch).max() < 1e-4 and (got2 < 0).any()
+
+
+def test_conv_f32_rows_with_bias_heads(_gpu):
+    # merged 1x1 heads: 512 -> 14+28+364 = 406 with bias, fp32 rows out (res3d_* layers)
+    rng = np.random.default_rng(8)
+    n, ci, co, h, w = 1, 512, 406, 9, 14
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, 1, 1)) * 0.01).astype(np.float32)
+    bias = rng.normal(0, 0.1, co).astype(np.float32)
+    ref = caffe_ref.convolution(x, wt, bias, 1, 0, 1)
+    rows = _gpu.conv_bn(x, wt, np.ones(co, np.float32), bias, relu=False, f32_rows=True)
+    got = rows[:, :co].reshape(n, h, w, co).transpose(0, 3, 1, 2)
+    assert np.abs(got - ref).max() < 1e-5
+    assert np.all(rows[:, co:] == 0)
+
+
+def test_linearity_property_full_size(_gpu):
+    # size-independent property at a BASELINE-size tile count: conv(x1 + x2) == conv(x1) + conv(x2)
+    rng = np.random.default_rng(9)
+    n, ci, co, h, w = 1, 512, 512, 45, 80          # res5 map of one 720p image
+    wt = (rng.standard_normal((co, ci, 3, 3)) * np.sqrt(2.0 / (ci * 9))).astype(np.float32)
+    x1 = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    x2 = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    one, zero = np.ones(co, np.float32), np.zeros(co, np.float32)
+    y1 = _gpu.conv_bn(x1, wt, one, zero, pad=2, dil=2, relu=False)
+    y2 = _gpu.conv_bn(x2, wt, one, zero, pad=2, dil=2, relu=False)
+    y12 = _gpu.conv_bn(x1 + x2, wt, one, zero, pad=2, dil=2, relu=False)
+    assert np.abs(y12 - (y1 + y2)).max() < 2e-4
+    # and a spot check of 64 random outputs against a float64 dot product
+    xp = np.pad(x1, ((0, 0), (0, 0), (2, 2), (2, 2)))
+    for _ in range(64):
+        c, yy, xx = rng.integers(co), rng.integers(h), rng.integers(w)
+        patch = xp[0, :, yy:yy + 5:2, xx:xx + 5:2].astype(np.float64)
+        assert abs((patch * wt[c]).sum() - y1[0, c, yy, xx]) < 1e-4
+
+
+def test_conv1_stem(_gpu):
+    L = libdc.lib()
+    rng = np.random.default_rng(10)
+    for (n, h, w) in ((1, 64, 64), (2, 75, 101)):
+        x = dcutil.synth.images(n, h, w, seed=3)
+        wt = (rng.standard_normal((64, 3, 7, 7)) * np.sqrt(2.0 / 147)).astype(np.float32)
+        a, b = _bn_params(rng, 64)
+        a = (a / 70).astype(np.float32)
+        ref = np.maximum(caffe_ref.convolution(x, wt, None, 2, 3, 1) * a.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1), 0)
+        wp = np.zeros((147, 64), np.float32)
+        libdc.check(L.dc_pack_conv1_weight(dcutil.ptr(wt), dcutil.ptr(wp)))
+        ho, wo = ref.shape[2:]
+        out = torch.full((2, n, ho, wo, 64), float("nan"), dtype=torch.float16, device="cuda")
+        dx, dw, da, db = _gpu.dev(x), _gpu.dev(wp), _gpu.dev(a), _gpu.dev(b)
+        libdc.check(L.dc_conv1_forward(dx.data_ptr(), n, h, w, dw.data_ptr(), da.data_ptr(), db.data_ptr(),
+                                       out.data_ptr(), _gpu.stream_ptr()))
+        torch.cuda.synchronize()
+        got = dcutil.np_join(out.cpu().numpy())
+        assert np.abs(got - ref).max() < 1e-4, np.abs(got - ref).max()
+
+
+def test_maxpool_bit_exact(_gpu):
+    L = libdc.lib()
+    rng = np.random.default_rng(11)
+    for (n, c, h, w) in ((1, 64, 32, 32), (2, 64, 37, 50), (1, 8, 5, 3)):
+        x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+        xs = dcutil.np_split(x)
+        xj = dcutil.np_join(xs)                      # the values the kernel actually sees
+        ref = caffe_ref.max_pool(xj, 3, 2)
+        ho, wo = ref.shape[2:]
+        assert (ho, wo) == (L.dc_pool_out_size(h, 3, 2), L.dc_pool_out_size(w, 3, 2))
+        out = torch.zeros((2, n, ho, wo, c), dtype=torch.float16, device="cuda")
+        dx = _gpu.dev(xs)
+        libdc.check(L.dc_maxpool_forward(dx.data_ptr(), n, h, w, c, 3, 2, out.data_ptr(), _gpu.stream_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(dcutil.np_join(out.cpu().numpy()), ref)
+
+
+def test_subsample_and_layout_roundtrip(_gpu):
+    L = libdc.lib()
+    rng = np.random.default_rng(12)
+    n, c, h, w = 2, 256, 13, 18
+    x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    dx = _gpu.dev(x)
+    sp = torch.zeros((2, n, h, w, c), dtype=torch.float16, device="cuda")
+    libdc.check(L.dc_nchw_to_split(dx.data_ptr(), n, c, h, w, sp.data_ptr(), _gpu.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(sp.cpu().numpy().view(np.uint16), dcutil.np_split(x).view(np.uint16))
+    back = torch.zeros((n, c, h, w), dtype=torch.float32, device="cuda")
+    libdc.check(L.dc_split_to_nchw(sp.data_ptr(), n, c, h, w, back.data_ptr(), _gpu.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy(), dcutil.np_join(dcutil.np_split(x)))
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    sub = torch.zeros((2, n, ho, wo, c), dtype=torch.float16, device="cuda")
+    libdc.check(L.dc_subsample_forward(sp.data_ptr(), n, h, w, c, 2, sub.data_ptr(), _gpu.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(sub.cpu().numpy(), sp.cpu().numpy()[:, :, ::2, ::2, :])
+
+
+def test_deconv_head_pipeline(_gpu):
+    """Deconvolution 3x3/2 + Crop + Eltwise(+1x1 skip conv with bias) + Sigmoid, as three ABI calls,
+    vs the oracle's layer-by-layer result (deconv_layer.cpp, crop_layer.cpp, eltwise, sigmoid)."""
+    L = libdc.lib()
+    rng = np.random.default_rng(13)
+    n, c5, c3, h, w = 2, 256, 128, 6, 7
+    heads = (("pose", 14, True), ("locref", 28, False))
+    x5 = np.maximum(rng.standard_normal((n, c5, h, w)), 0).astype(np.float32)
+    x3 = np.maximum(rng.standard_normal((n, c3, 2 * h, 2 * w)), 0).astype(np.float32)
+    wd = [(rng.standard_normal((c5, co, 3, 3)) * 0.05).astype(np.float32) for _, co, _ in heads]
+    bd = [rng.normal(0, 0.1, co).astype(np.float32) for _, co, _ in heads]
+    ws = [(rng.standard_normal((co, c3, 1, 1)) * 0.05).astype(np.float32) for _, co, _ in heads]
+    bs = [rng.normal(0, 0.1, co).astype(np.float32) for _, co, _ in heads]
+    # merged GEMMs
+    wd_all = np.concatenate(wd, axis=1)
+    ws_all = np.concatenate(ws, axis=0)
+    ctot = wd_all.shape[1]
+    packed, rs = dcutil.pack_deconv(wd_all)
+    rows = packed.shape[1]
+    x5s = _gpu.dev(dcutil.np_split(x5))
+    col = torch.zeros((n * h * w, rows), dtype=torch.float32, device="cuda")
+    dwp, dsc, dsh = _gpu.dev(packed), _gpu.dev(rs), _gpu.dev(np.zeros(rows, np.float32))
+    args = libdc.ConvArgs(x=x5s.data_ptr(), n=n, h=h, w=w, cin=c5, cout=ctot * 9, kh=1, kw=1, pad=0, dilation=1,
+                          w_packed=dwp.data_ptr(), scale=dsc.data_ptr(), shift=dsh.data_ptr(), residual=None,
+                          relu=0, out_f32_rows=1, ldc=rows, out=col.data_ptr())
+    libdc.check(L.dc_conv_forward(C.byref(args), _gpu.stream_ptr()))
+    skip_rows = _gpu.conv_bn(x3, ws_all, np.ones(ctot, np.float32), np.concatenate(bs) + np.concatenate(bd),
+                             relu=False, f32_rows=True)
+    dskip = _gpu.dev(skip_rows)
+    off = 0
+    for i, (name, co, sig) in enumerate(heads):
+        up = caffe_ref.deconvolution(x5, wd[i], bd[i], 2, 0, 1)
+        sk = caffe_ref.convolution(x3, ws[i], bs[i], 1, 0, 1)
+        ref = caffe_ref.eltwise_sum([sk, caffe_ref.crop(up, sk)])
+        if sig:
+            ref = caffe_ref.sigmoid(ref)
+        out = torch.zeros((n, co, 2 * h, 2 * w), dtype=torch.float32, device="cuda")
+        libdc.check(L.dc_head_finish(col.data_ptr(), rows, off * 9, dskip.data_ptr(), skip_rows.shape[1], off,
+                                     out.data_ptr(), n, co, h, w, 2 * h, 2 * w, int(sig), _gpu.stream_ptr()))
+        torch.cuda.synchronize()
+        assert np.abs(out.cpu().numpy() - ref).max() < 2e-5, name
+        off += co
+
+
+def test_launch_counter_moves(_gpu):
+    before = libdc.lib().dc_launch_count()
+    test_subsample_and_layout_roundtrip(_gpu)
+    assert libdc.lib().dc_launch_count() >= before + 3
