@@ -1,0 +1,120 @@
+// Net<Dtype>: prototxt -> DAG of layers and named blobs; public API of the reference's
+// include/caffe/net.hpp:24-313 for the inference path (Init, Forward*, Reshape,
+// CopyTrainedLayersFrom, ToProto, name tables).  In GPU mode ForwardPrefilled runs the fused
+// B200 plan (dc_engine.hpp) over the same blobs; Net::set_fusion(false) or a topology the planner
+// does not recognise falls back to per-layer Layer::Forward (still CUDA, never CPU).
+#pragma once
+#include "caffe/blob.hpp"
+#include "caffe/common.hpp"
+#include "caffe/layer.hpp"
+#include "caffe/proto/caffe.pb.h"
+
+namespace caffe {
+
+class FusedPlan;
+
+template <typename Dtype>
+class Net {
+ public:
+  explicit Net(const NetParameter& param, const Net* root_net = NULL);
+  explicit Net(const string& param_file, Phase phase, const Net* root_net = NULL);
+  virtual ~Net();
+
+  void Init(const NetParameter& param);
+
+  const vector<Blob<Dtype>*>& ForwardPrefilled(Dtype* loss = NULL);
+  Dtype ForwardFromTo(int start, int end);
+  Dtype ForwardFrom(int start) { return ForwardFromTo(start, static_cast<int>(layers_.size()) - 1); }
+  Dtype ForwardTo(int end) { return ForwardFromTo(0, end); }
+  const vector<Blob<Dtype>*>& Forward(const vector<Blob<Dtype>*>& bottom, Dtype* loss = NULL);
+  const vector<Blob<Dtype>*>& Forward(Dtype* loss = NULL) { return ForwardPrefilled(loss); }
+
+  void Reshape();
+  void ShareTrainedLayersWith(const Net* other);
+  void CopyTrainedLayersFrom(const NetParameter& param);
+  void CopyTrainedLayersFrom(const string trained_filename);
+  void CopyTrainedLayersFromBinaryProto(const string trained_filename);
+  void ToProto(NetParameter* param, bool write_diff = false) const;
+
+  inline const string& name() const { return name_; }
+  inline const vector<string>& layer_names() const { return layer_names_; }
+  inline const vector<string>& blob_names() const { return blob_names_; }
+  inline const vector<shared_ptr<Blob<Dtype> > >& blobs() const { return blobs_; }
+  inline const vector<shared_ptr<Layer<Dtype> > >& layers() const { return layers_; }
+  inline Phase phase() const { return phase_; }
+  inline const vector<vector<Blob<Dtype>*> >& bottom_vecs() const { return bottom_vecs_; }
+  inline const vector<vector<Blob<Dtype>*> >& top_vecs() const { return top_vecs_; }
+  inline const vector<vector<int> >& bottom_ids() const { return bottom_id_vecs_; }
+  inline const vector<vector<int> >& top_ids() const { return top_id_vecs_; }
+  inline const vector<int>& top_ids(int i) const { return top_id_vecs_[i]; }
+  inline const vector<int>& bottom_ids(int i) const { return bottom_id_vecs_[i]; }
+  inline const vector<shared_ptr<Blob<Dtype> > >& params() const { return params_; }
+  inline const vector<Blob<Dtype>*>& learnable_params() const { return learnable_params_; }
+  inline int num_inputs() const { return static_cast<int>(net_input_blobs_.size()); }
+  inline int num_outputs() const { return static_cast<int>(net_output_blobs_.size()); }
+  inline const vector<Blob<Dtype>*>& input_blobs() const { return net_input_blobs_; }
+  inline const vector<Blob<Dtype>*>& output_blobs() const { return net_output_blobs_; }
+  inline const vector<int>& input_blob_indices() const { return net_input_blob_indices_; }
+  inline const vector<int>& output_blob_indices() const { return net_output_blob_indices_; }
+  bool has_blob(const string& blob_name) const;
+  const shared_ptr<Blob<Dtype> > blob_by_name(const string& blob_name) const;
+  bool has_layer(const string& layer_name) const;
+  const shared_ptr<Layer<Dtype> > layer_by_name(const string& layer_name) const;
+  void set_debug_info(const bool value) { debug_info_ = value; }
+
+  static void FilterNet(const NetParameter& param, NetParameter* param_filtered);
+  static bool StateMeetsRule(const NetState& state, const NetStateRule& rule, const string& layer_name);
+
+  // ---- B200 extensions (not in the reference) ----
+  // Fused plan on/off (default on in GPU mode).  With fusion the blobs of fused-away intermediates
+  // are not written unless materialize_intermediates(true) asks for every named blob to be filled
+  // with its Caffe-final value (the value the in-place BN/Scale/ReLU chain would have left there).
+  void set_fusion(bool on);
+  bool fusion() const { return fusion_; }
+  void materialize_intermediates(bool on);
+  bool fused_last_forward() const { return fused_last_forward_; }
+  // Why the planner declined (empty when the fused plan is active).
+  const string& fusion_diagnostic() const { return fusion_diag_; }
+  // Device kernels launched by the last ForwardPrefilled.
+  long long last_forward_launches() const { return last_launches_; }
+  void InvalidatePlan();
+
+ protected:
+  void AppendTop(const NetParameter& param, const int layer_id, const int top_id, set<string>* available_blobs, map<string, int>* blob_name_to_idx);
+  int AppendBottom(const NetParameter& param, const int layer_id, const int bottom_id, set<string>* available_blobs, map<string, int>* blob_name_to_idx);
+  void AppendParam(const NetParameter& param, const int layer_id, const int param_id);
+  void ForwardDebugInfo(const int layer_id);
+
+  string name_;
+  Phase phase_;
+  vector<shared_ptr<Layer<Dtype> > > layers_;
+  vector<string> layer_names_;
+  map<string, int> layer_names_index_;
+  vector<shared_ptr<Blob<Dtype> > > blobs_;
+  vector<string> blob_names_;
+  map<string, int> blob_names_index_;
+  vector<vector<Blob<Dtype>*> > bottom_vecs_;
+  vector<vector<int> > bottom_id_vecs_;
+  vector<vector<Blob<Dtype>*> > top_vecs_;
+  vector<vector<int> > top_id_vecs_;
+  vector<int> net_input_blob_indices_;
+  vector<int> net_output_blob_indices_;
+  vector<Blob<Dtype>*> net_input_blobs_;
+  vector<Blob<Dtype>*> net_output_blobs_;
+  vector<shared_ptr<Blob<Dtype> > > params_;
+  vector<Blob<Dtype>*> learnable_params_;
+  bool debug_info_ = false;
+  NetParameter filtered_param_;     // post FilterNet + InsertSplits
+
+  bool fusion_ = true;
+  bool materialize_ = false;
+  bool fused_last_forward_ = false;
+  string fusion_diag_;
+  long long last_launches_ = 0;
+  FusedPlan* plan_ = nullptr;
+  vector<vector<int> > plan_input_shapes_;
+
+  DISABLE_COPY_AND_ASSIGN(Net);
+};
+
+}  // namespace caffe

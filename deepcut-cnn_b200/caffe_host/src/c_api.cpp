@@ -1,0 +1,132 @@
+// C ABI over the C++ Caffe host, for the Python `caffe` shim (python/caffe/_caffe.cpp in the
+// reference is a boost.python module over the same classes; boost is not in this image, so the
+// binding is ctypes over these functions).  Every call catches the host's CHECK failures
+// (caffe::FatalError) and turns them into a non-zero return + caffe_last_error().
+#include <cstring>
+#include <string>
+
+#include "caffe/caffe.hpp"
+#include "caffe/dc_engine.hpp"
+#include "caffe_b200_c.h"
+
+using namespace caffe;  // NOLINT
+
+namespace {
+thread_local std::string g_error;
+struct BlobHandle { shared_ptr<Blob<float> > blob; };
+
+template <class F>
+int Guard(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+Net<float>* N(void* h) { return static_cast<Net<float>*>(h); }
+Blob<float>* B(void* h) { return static_cast<BlobHandle*>(h)->blob.get(); }
+}  // namespace
+
+extern "C" {
+
+const char* caffe_last_error(void) { return g_error.c_str(); }
+
+int caffe_set_mode(int gpu) { return Guard([&] { Caffe::set_fatal_throws(true); Caffe::set_mode(gpu ? Caffe::GPU : Caffe::CPU); }); }
+int caffe_get_mode(void) { return Caffe::mode() == Caffe::GPU; }
+int caffe_set_device(int id) { return Guard([&] { Caffe::set_fatal_throws(true); Caffe::SetDevice(id); }); }
+int caffe_device_count(void) { return Caffe::device_count(); }
+void caffe_set_log_level(int level) { Caffe::set_log_level(level); }
+void* caffe_stream(void) { void* s = nullptr; Guard([&] { s = Caffe::stream(); }); return s; }
+int caffe_sync(void) { return Guard([&] { DC_CHECK(dc_stream_sync(Caffe::stream())); }); }
+
+void* caffe_net_create(const char* prototxt, int phase) {
+  Net<float>* net = nullptr;
+  Caffe::set_fatal_throws(true);
+  if (Guard([&] { net = new Net<float>(std::string(prototxt), phase == 0 ? TRAIN : TEST); })) return nullptr;
+  return net;
+}
+void* caffe_net_create_from_string(const char* prototxt_text, int phase) {
+  Net<float>* net = nullptr;
+  Caffe::set_fatal_throws(true);
+  if (Guard([&] {
+        NetParameter p;
+        std::string err;
+        CHECK(p.ParseFromTextString(prototxt_text, &err)) << "prototxt: " << err;
+        p.mutable_state()->set_phase(phase == 0 ? TRAIN : TEST);
+        net = new Net<float>(p);
+      }))
+    return nullptr;
+  return net;
+}
+void caffe_net_destroy(void* net) { delete N(net); }
+int caffe_net_copy_trained_from(void* net, const char* file) { return Guard([&] { N(net)->CopyTrainedLayersFrom(std::string(file)); }); }
+int caffe_net_save(void* net, const char* file) {
+  return Guard([&] { NetParameter p; N(net)->ToProto(&p, false); WriteProtoToBinaryFile(p, file); });
+}
+int caffe_net_forward(void* net) { return Guard([&] { N(net)->ForwardPrefilled(); }); }
+int caffe_net_forward_from_to(void* net, int start, int end) { return Guard([&] { N(net)->ForwardFromTo(start, end); }); }
+int caffe_net_reshape(void* net) { return Guard([&] { N(net)->Reshape(); }); }
+const char* caffe_net_name(void* net) { return N(net)->name().c_str(); }
+
+int caffe_net_num_blobs(void* net) { return static_cast<int>(N(net)->blobs().size()); }
+const char* caffe_net_blob_name(void* net, int i) { return N(net)->blob_names()[i].c_str(); }
+int caffe_net_num_layers(void* net) { return static_cast<int>(N(net)->layers().size()); }
+const char* caffe_net_layer_name(void* net, int i) { return N(net)->layer_names()[i].c_str(); }
+const char* caffe_net_layer_type(void* net, int i) { return N(net)->layers()[i]->type(); }
+int caffe_net_layer_num_blobs(void* net, int i) { return static_cast<int>(N(net)->layers()[i]->blobs().size()); }
+int caffe_net_layer_num_bottoms(void* net, int i) { return static_cast<int>(N(net)->bottom_ids(i).size()); }
+int caffe_net_layer_bottom_id(void* net, int i, int j) { return N(net)->bottom_ids(i)[j]; }
+int caffe_net_layer_num_tops(void* net, int i) { return static_cast<int>(N(net)->top_ids(i).size()); }
+int caffe_net_layer_top_id(void* net, int i, int j) { return N(net)->top_ids(i)[j]; }
+int caffe_net_num_inputs(void* net) { return N(net)->num_inputs(); }
+int caffe_net_input_index(void* net, int i) { return N(net)->input_blob_indices()[i]; }
+int caffe_net_num_outputs(void* net) { return N(net)->num_outputs(); }
+int caffe_net_output_index(void* net, int i) { return N(net)->output_blob_indices()[i]; }
+int caffe_net_layer_weights_changed(void* net, int i) {
+  return Guard([&] { N(net)->layers()[i]->OnWeightsChanged(); N(net)->InvalidatePlan(); });
+}
+
+void* caffe_net_blob(void* net, int i) {
+  BlobHandle* h = new BlobHandle();
+  h->blob = N(net)->blobs()[i];
+  return h;
+}
+void* caffe_net_layer_blob(void* net, int layer, int j) {
+  BlobHandle* h = new BlobHandle();
+  h->blob = N(net)->layers()[layer]->blobs()[j];
+  return h;
+}
+void caffe_blob_release(void* blob) { delete static_cast<BlobHandle*>(blob); }
+int caffe_blob_num_axes(void* blob) { return B(blob)->num_axes(); }
+int caffe_blob_shape(void* blob, int axis) { return B(blob)->shape(axis); }
+int caffe_blob_count(void* blob) { return B(blob)->count(); }
+int caffe_blob_reshape(void* blob, int naxes, const int* dims) {
+  return Guard([&] { B(blob)->Reshape(vector<int>(dims, dims + naxes)); });
+}
+float* caffe_blob_mutable_cpu_data(void* blob) { float* p = nullptr; Guard([&] { p = B(blob)->mutable_cpu_data(); }); return p; }
+const float* caffe_blob_cpu_data(void* blob) { const float* p = nullptr; Guard([&] { p = B(blob)->cpu_data(); }); return p; }
+float* caffe_blob_mutable_cpu_diff(void* blob) { float* p = nullptr; Guard([&] { p = B(blob)->mutable_cpu_diff(); }); return p; }
+const float* caffe_blob_gpu_data(void* blob) { const float* p = nullptr; Guard([&] { p = B(blob)->gpu_data(); }); return p; }
+float* caffe_blob_mutable_gpu_data(void* blob) { float* p = nullptr; Guard([&] { p = B(blob)->mutable_gpu_data(); }); return p; }
+
+int caffe_net_set_fusion(void* net, int on) { return Guard([&] { N(net)->set_fusion(on != 0); }); }
+int caffe_net_materialize_intermediates(void* net, int on) { return Guard([&] { N(net)->materialize_intermediates(on != 0); }); }
+int caffe_net_fused_last_forward(void* net) { return N(net)->fused_last_forward(); }
+const char* caffe_net_fusion_diagnostic(void* net) { return N(net)->fusion_diagnostic().c_str(); }
+long long caffe_net_last_forward_launches(void* net) { return N(net)->last_forward_launches(); }
+
+int caffe_insert_splits_text(const char* prototxt_text, char* out, int out_cap) {
+  return Guard([&] {
+    NetParameter p, q;
+    std::string err;
+    CHECK(p.ParseFromTextString(prototxt_text, &err)) << "prototxt: " << err;
+    InsertSplits(p, &q);
+    const std::string s = q.DebugString();
+    CHECK_LT((int)s.size(), out_cap) << "output buffer too small";
+    memcpy(out, s.c_str(), s.size() + 1);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,665 @@
+#include "caffe/dc_engine.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <sstream>
+
+#include "caffe/layers/dc_layers.hpp"
+#include "deepcut_b200.h"
+
+namespace caffe {
+
+typedef BaseConvolutionLayer<float> ConvBase;
+
+// A value flowing through the net.  In-place layers create a new Tensor on the same blob; Split
+// tops alias their bottom's Tensor.
+struct FusedPlan::Tensor {
+  enum Kind { kBlobF32, kSplit, kF32Rows, kVirtual } kind = kVirtual;
+  int id = 0;
+  int n = 0, c = 0, h = 0, w = 0;
+  int ld = 0;                         // kF32Rows: row stride (floats); rows = n*h*w
+  int blob = -1;                      // Net blob that names this value (-1: internal)
+  int producer_layer = -1;            // -1: net input
+  std::vector<int> consumers;         // layer ids reading it (Split layers excluded)
+  int def_step = -1, last_step = -1;  // liveness in step indices
+  size_t bytes = 0, offset = 0;       // arena placement
+  void* ptr = nullptr;                // resolved device address (arena tensors)
+  size_t elems() const { return static_cast<size_t>(n) * c * h * w; }
+};
+
+struct FusedPlan::Step {
+  enum Type { kConv1, kConvBN, kSubsample, kMaxPool, kHeadGemm, kHeadFinish, kToBlob } type = kConvBN;
+  std::string name;
+  Tensor* in = nullptr;
+  Tensor* in2 = nullptr;              // residual (kConvBN) / skip rows (kHeadFinish)
+  Tensor* out = nullptr;
+  // convolution
+  int conv_layer = -1, bn_layer = -1, scale_layer = -1;
+  bool relu = false;
+  int kh = 1, kw = 1, pad = 0, dil = 1, stride = 1, cout = 0;
+  bool deconv_rows = false;           // kHeadGemm over deconv weights
+  std::vector<int> merged_layers;     // kHeadGemm: layers whose weights are concatenated
+  void* w_dev = nullptr;
+  float* scale_dev = nullptr;
+  float* shift_dev = nullptr;
+  // head finish
+  int col_off = 0, skip_off = 0, sigmoid = 0, out_blob = -1;
+  Tensor* col = nullptr;
+  // pooling
+  int pool_k = 3, pool_s = 2;
+};
+
+FusedPlan::~FusedPlan() {
+  for (Tensor* t : tensors_) delete t;
+  for (Step* s : steps_) delete s;
+  for (void* p : weight_allocs_) dc_free(p);
+  if (arena_) dc_free(arena_);
+}
+
+namespace {
+
+template <class L>
+L* As(Layer<float>* l) { return dynamic_cast<L*>(l); }
+
+struct Matcher {
+  Net<float>& net;
+  std::vector<FusedPlan::Tensor*>& tensors;
+  std::vector<FusedPlan::Step*>& steps;
+  std::vector<int> cur;                       // blob index -> tensor id currently held
+  std::vector<std::vector<int> > bot_t, top_t;   // per layer tensor ids
+  std::vector<char> done;
+  std::string why;
+
+  Matcher(Net<float>& n, std::vector<FusedPlan::Tensor*>& t, std::vector<FusedPlan::Step*>& s) : net(n), tensors(t), steps(s) {}
+
+  FusedPlan::Tensor* NewTensor(int blob, int producer) {
+    FusedPlan::Tensor* t = new FusedPlan::Tensor();
+    t->id = static_cast<int>(tensors.size());
+    t->blob = blob;
+    t->producer_layer = producer;
+    if (blob >= 0) {
+      const Blob<float>& b = *net.blobs()[blob];
+      if (b.num_axes() == 4) { t->n = b.shape(0); t->c = b.shape(1); t->h = b.shape(2); t->w = b.shape(3); }
+    }
+    tensors.push_back(t);
+    return t;
+  }
+  FusedPlan::Tensor* NewInternal(FusedPlan::Tensor::Kind k, int n, int c, int h, int w) {
+    FusedPlan::Tensor* t = NewTensor(-1, -2);
+    t->kind = k; t->n = n; t->c = c; t->h = h; t->w = w;
+    return t;
+  }
+  bool Fail(const std::string& m) { why = m; return false; }
+
+  void BuildDataflow() {
+    const int nl = static_cast<int>(net.layers().size());
+    cur.assign(net.blobs().size(), -1);
+    bot_t.resize(nl);
+    top_t.resize(nl);
+    done.assign(nl, 0);
+    for (int idx : net.input_blob_indices()) {
+      FusedPlan::Tensor* t = NewTensor(idx, -1);
+      t->kind = FusedPlan::Tensor::kBlobF32;
+      cur[idx] = t->id;
+    }
+    for (int i = 0; i < nl; ++i) {
+      const bool is_split = std::string(net.layers()[i]->type()) == "Split";
+      for (int b : net.bottom_ids(i)) {
+        bot_t[i].push_back(cur[b]);
+        if (!is_split) tensors[cur[b]]->consumers.push_back(i);
+      }
+      for (int b : net.top_ids(i)) {
+        if (is_split) { cur[b] = bot_t[i][0]; top_t[i].push_back(cur[b]); continue; }
+        FusedPlan::Tensor* t = NewTensor(b, i);
+        cur[b] = t->id;
+        top_t[i].push_back(t->id);
+      }
+    }
+    // values still held by output blobs are consumed by the caller
+    for (int idx : net.output_blob_indices()) tensors[cur[idx]]->consumers.push_back(-1);
+  }
+
+  // the single consumer of tensor t if it is layer type `type` operating in place, else -1
+  int InPlaceNext(int t, const char* type) {
+    const std::vector<int>& c = tensors[t]->consumers;
+    if (c.size() != 1 || c[0] < 0) return -1;
+    const int j = c[0];
+    if (std::string(net.layers()[j]->type()) != type) return -1;
+    if (net.bottom_ids(j).size() != 1 || net.top_ids(j).size() != 1 || net.bottom_ids(j)[0] != net.top_ids(j)[0]) return -1;
+    return j;
+  }
+
+  FusedPlan::Step* AddStep(FusedPlan::Step::Type type, const std::string& name) {
+    FusedPlan::Step* s = new FusedPlan::Step();
+    s->type = type;
+    s->name = name;
+    steps.push_back(s);
+    return s;
+  }
+
+  std::map<std::pair<int, int>, FusedPlan::Tensor*> subsampled;   // (tensor, stride) -> gathered tensor
+
+  bool MatchConv(int i) {
+    ConvBase* conv = As<ConvBase>(net.layers()[i].get());
+    const std::string lname = net.layer_names()[i];
+    if (net.bottom_ids(i).size() != 1) return Fail("convolution " + lname + " has several bottoms");
+    FusedPlan::Tensor* in = tensors[bot_t[i][0]];
+    int t = top_t[i][0];
+    int bn = InPlaceNext(t, "BatchNorm");
+    if (bn >= 0) t = top_t[bn][0];
+    int sc = InPlaceNext(t, "Scale");
+    if (sc >= 0) t = top_t[sc][0];
+    int rl = InPlaceNext(t, "ReLU");
+    if (rl >= 0) {
+      if (net.layers()[rl]->layer_param().relu_param().negative_slope() != 0.f) rl = -1;   // leaky: leave to the per-layer path
+      else t = top_t[rl][0];
+    }
+    if (conv->kernel_h() != conv->kernel_w() || conv->pad_h() != conv->pad_w() || conv->stride_h() != conv->stride_w() ||
+        conv->dilation_h() != conv->dilation_w())
+      return Fail("convolution " + lname + " is not square");
+    const int k = conv->kernel_h(), s = conv->stride_h(), p = conv->pad_h(), d = conv->dilation_h();
+    FusedPlan::Tensor* out = tensors[t];
+    done[i] = 1;
+    if (bn >= 0) done[bn] = 1;
+    if (sc >= 0) done[sc] = 1;
+    if (rl >= 0) done[rl] = 1;
+    // intermediate in-place values (conv raw output, post-BN, ...) never exist
+    for (int v = top_t[i][0]; v != t;) {
+      tensors[v]->kind = FusedPlan::Tensor::kVirtual;
+      v = top_t[tensors[v]->consumers[0]][0];
+    }
+    if (in->kind == FusedPlan::Tensor::kBlobF32) {
+      if (!(in->c == 3 && k == 7 && s == 2 && p == 3 && d == 1 && conv->num_output() == 64 && rl >= 0 && !conv->bias_term()))
+        return Fail("convolution " + lname + " reads an fp32 blob but is not the 7x7/2 3->64 stem");
+      FusedPlan::Step* st = AddStep(FusedPlan::Step::kConv1, lname);
+      st->in = in; st->out = out; st->conv_layer = i; st->bn_layer = bn; st->scale_layer = sc; st->relu = true;
+      st->cout = 64;
+      out->kind = FusedPlan::Tensor::kSplit;
+      return true;
+    }
+    if (in->kind != FusedPlan::Tensor::kSplit) return Fail("convolution " + lname + " input is not a split-NHWC activation");
+    if (in->c % 64 != 0) return Fail("convolution " + lname + ": cin not a multiple of 64");
+    if (conv->num_output() % 32 != 0) return Fail("convolution " + lname + ": cout not a multiple of 32");
+    if (k * k > 9) return Fail("convolution " + lname + ": more than 9 taps");
+    if (conv->bias_term() && (bn >= 0 || sc >= 0)) return Fail("convolution " + lname + ": bias followed by BatchNorm");
+    if (s != 1) {
+      if (!(k == 1 && p == 0)) return Fail("convolution " + lname + ": stride > 1 only for 1x1 pad 0");
+      const std::pair<int, int> key(in->id, s);
+      if (!subsampled.count(key)) {
+        FusedPlan::Tensor* g = NewInternal(FusedPlan::Tensor::kSplit, in->n, in->c, (in->h - 1) / s + 1, (in->w - 1) / s + 1);
+        FusedPlan::Step* ss = AddStep(FusedPlan::Step::kSubsample, lname + "/gather");
+        ss->in = in; ss->out = g; ss->stride = s;
+        subsampled[key] = g;
+      }
+      in = subsampled[key];
+    }
+    FusedPlan::Step* st = AddStep(FusedPlan::Step::kConvBN, lname);
+    st->in = in; st->out = out; st->conv_layer = i; st->bn_layer = bn; st->scale_layer = sc; st->relu = rl >= 0;
+    st->kh = st->kw = k; st->pad = p; st->dil = d; st->cout = conv->num_output();
+    out->kind = FusedPlan::Tensor::kSplit;
+    return true;
+  }
+
+  int StepProducing(FusedPlan::Tensor* t) {
+    for (int s = static_cast<int>(steps.size()) - 1; s >= 0; --s)
+      if (steps[s]->out == t) return s;
+    return -1;
+  }
+
+  bool MatchEltwise(int i) {
+    EltwiseLayer<float>* e = As<EltwiseLayer<float> >(net.layers()[i].get());
+    const std::string lname = net.layer_names()[i];
+    if (bot_t[i].size() != 2 || e->coeffs()[0] != 1.f || e->coeffs()[1] != 1.f) return Fail("eltwise " + lname + " is not a plain 2-input sum");
+    // which bottom is the branch (a ConvBN output without ReLU, read only here)?
+    for (int side = 1; side >= 0; --side) {
+      FusedPlan::Tensor* branch = tensors[bot_t[i][side]];
+      FusedPlan::Tensor* other = tensors[bot_t[i][1 - side]];
+      const int sb = StepProducing(branch);
+      if (sb < 0 || steps[sb]->type != FusedPlan::Step::kConvBN || steps[sb]->relu || steps[sb]->in2 != nullptr) continue;
+      if (branch->consumers.size() != 1 || other->kind != FusedPlan::Tensor::kSplit) continue;
+      const int so = StepProducing(other);
+      if (so >= sb) continue;                 // shortcut must exist before the branch conv runs
+      int t = top_t[i][0];
+      const int rl = InPlaceNext(t, "ReLU");
+      if (rl >= 0 && net.layers()[rl]->layer_param().relu_param().negative_slope() == 0.f) {
+        tensors[t]->kind = FusedPlan::Tensor::kVirtual;
+        t = top_t[rl][0];
+        done[rl] = 1;
+        steps[sb]->relu = true;
+      }
+      branch->kind = FusedPlan::Tensor::kVirtual;
+      steps[sb]->in2 = other;
+      steps[sb]->out = tensors[t];
+      steps[sb]->name += "+" + lname;
+      tensors[t]->kind = FusedPlan::Tensor::kSplit;
+      done[i] = 1;
+      return true;
+    }
+    return Fail("eltwise " + lname + " does not close a residual branch the conv epilogue can absorb");
+  }
+
+  bool MatchPool(int i) {
+    PoolingLayer<float>* pl = As<PoolingLayer<float> >(net.layers()[i].get());
+    const std::string lname = net.layer_names()[i];
+    FusedPlan::Tensor* in = tensors[bot_t[i][0]];
+    if (in->kind != FusedPlan::Tensor::kSplit) return Fail("pooling " + lname + " input is not a split-NHWC activation");
+    if (pl->kernel_h() != pl->kernel_w() || pl->stride_h() != pl->stride_w() || pl->pad_h() != 0 || pl->pad_w() != 0)
+      return Fail("pooling " + lname + ": only square, unpadded windows");
+    FusedPlan::Step* st = AddStep(FusedPlan::Step::kMaxPool, lname);
+    st->in = in; st->out = tensors[top_t[i][0]];
+    st->pool_k = pl->kernel_h(); st->pool_s = pl->stride_h();
+    st->out->kind = FusedPlan::Tensor::kSplit;
+    done[i] = 1;
+    return true;
+  }
+
+  // All heads  Deconvolution(X5) -> Crop(., skip) ; skip = Convolution1x1(X3) ; Eltwise(skip, crop) [; Sigmoid]
+  bool MatchHeads(int first) {
+    struct Head { int deconv, skipconv, crop, elt, sig; };
+    std::vector<Head> heads;
+    FusedPlan::Tensor* x5 = tensors[bot_t[first][0]];
+    FusedPlan::Tensor* x3 = nullptr;
+    const int nl = static_cast<int>(net.layers().size());
+    for (int d = first; d < nl; ++d) {
+      if (done[d] || std::string(net.layers()[d]->type()) != "Deconvolution" || tensors[bot_t[d][0]] != x5) continue;
+      ConvBase* dc = As<ConvBase>(net.layers()[d].get());
+      const std::string dn = net.layer_names()[d];
+      if (!(dc->kernel_h() == 3 && dc->kernel_w() == 3 && dc->stride_h() == 2 && dc->stride_w() == 2 && dc->pad_h() == 0 && dc->pad_w() == 0 &&
+            dc->dilation_h() == 1 && dc->dilation_w() == 1))
+        return Fail("deconvolution " + dn + " is not 3x3 stride 2 pad 0");
+      FusedPlan::Tensor* up = tensors[top_t[d][0]];
+      if (up->consumers.size() != 1 || up->consumers[0] < 0 || std::string(net.layers()[up->consumers[0]]->type()) != "Crop")
+        return Fail("deconvolution " + dn + " is not followed by Crop");
+      Head hd;
+      hd.deconv = d;
+      hd.crop = up->consumers[0];
+      CropLayer<float>* cl = As<CropLayer<float> >(net.layers()[hd.crop].get());
+      if (cl->crop_h() != 0 || cl->crop_w() != 0 || bot_t[hd.crop][0] != up->id) return Fail("crop after " + dn + " has non-zero offsets");
+      FusedPlan::Tensor* skip = tensors[bot_t[hd.crop][1]];
+      hd.skipconv = skip->producer_layer;
+      if (hd.skipconv < 0 || std::string(net.layers()[hd.skipconv]->type()) != "Convolution") return Fail("crop reference of " + dn + " is not a convolution output");
+      ConvBase* sk = As<ConvBase>(net.layers()[hd.skipconv].get());
+      if (!(sk->kernel_h() == 1 && sk->kernel_w() == 1 && sk->stride_h() == 1 && sk->pad_h() == 0 && sk->num_output() == dc->num_output()))
+        return Fail("skip head of " + dn + " is not a 1x1 convolution with matching outputs");
+      FusedPlan::Tensor* sin = tensors[bot_t[hd.skipconv][0]];
+      if (x3 == nullptr) x3 = sin;
+      if (sin != x3 || sin->kind != FusedPlan::Tensor::kSplit) return Fail("heads do not share one skip input");
+      FusedPlan::Tensor* cropped = tensors[top_t[hd.crop][0]];
+      // skip is read by the crop (shape only) and the eltwise; cropped only by the eltwise
+      if (cropped->consumers.size() != 1 || cropped->consumers[0] < 0 || std::string(net.layers()[cropped->consumers[0]]->type()) != "Eltwise")
+        return Fail("crop of " + dn + " does not feed an Eltwise");
+      hd.elt = cropped->consumers[0];
+      EltwiseLayer<float>* e = As<EltwiseLayer<float> >(net.layers()[hd.elt].get());
+      if (bot_t[hd.elt].size() != 2 || e->coeffs()[0] != 1.f || e->coeffs()[1] != 1.f) return Fail("head eltwise is not a plain sum");
+      const int o0 = bot_t[hd.elt][0], o1 = bot_t[hd.elt][1];
+      if (!((o0 == skip->id && o1 == cropped->id) || (o1 == skip->id && o0 == cropped->id))) return Fail("head eltwise does not add skip and cropped deconv");
+      for (int c : skip->consumers) if (c != hd.crop && c != hd.elt) return Fail("skip head output has other readers");
+      hd.sig = -1;
+      FusedPlan::Tensor* sum = tensors[top_t[hd.elt][0]];
+      if (sum->consumers.size() == 1 && sum->consumers[0] >= 0 && std::string(net.layers()[sum->consumers[0]]->type()) == "Sigmoid") hd.sig = sum->consumers[0];
+      heads.push_back(hd);
+    }
+    if (heads.empty()) return Fail("no head matched");
+    int ctot = 0;
+    for (const Head& h : heads) ctot += As<ConvBase>(net.layers()[h.deconv].get())->num_output();
+    const int h5 = x5->h, w5 = x5->w, h3 = x3->h, w3 = x3->w;
+    if (!(2 * h5 + 1 > h3 && 2 * w5 + 1 > w3 && h3 <= 2 * h5 + 1)) return Fail("head geometry: crop larger than the deconvolution output");
+    // merged deconv GEMM -> col rows, merged 1x1 GEMM -> skip rows
+    FusedPlan::Tensor* col = NewInternal(FusedPlan::Tensor::kF32Rows, x5->n, dc_packed_rows(ctot * 9), h5, w5);
+    col->ld = dc_packed_rows(ctot * 9);
+    FusedPlan::Step* g1 = AddStep(FusedPlan::Step::kHeadGemm, "heads/deconv_gemm");
+    g1->in = x5; g1->out = col; g1->deconv_rows = true; g1->cout = ctot * 9;
+    FusedPlan::Tensor* srows = NewInternal(FusedPlan::Tensor::kF32Rows, x3->n, dc_packed_rows(ctot), h3, w3);
+    srows->ld = dc_packed_rows(ctot);
+    FusedPlan::Step* g2 = AddStep(FusedPlan::Step::kHeadGemm, "heads/skip_gemm");
+    g2->in = x3; g2->out = srows; g2->deconv_rows = false; g2->cout = ctot;
+    int off = 0;
+    for (const Head& h : heads) {
+      g1->merged_layers.push_back(h.deconv);
+      g2->merged_layers.push_back(h.skipconv);
+      const int co = As<ConvBase>(net.layers()[h.deconv].get())->num_output();
+      const int out_layer = h.sig >= 0 ? h.sig : h.elt;
+      FusedPlan::Tensor* out = tensors[top_t[out_layer][0]];
+      FusedPlan::Step* f = AddStep(FusedPlan::Step::kHeadFinish, net.layer_names()[out_layer]);
+      f->col = col; f->in2 = srows; f->in = x5; f->out = out; f->col_off = off * 9; f->skip_off = off; f->sigmoid = h.sig >= 0; f->cout = co;
+      out->kind = FusedPlan::Tensor::kBlobF32;
+      f->out_blob = out->blob;
+      // fused-away values
+      tensors[top_t[h.deconv][0]]->kind = FusedPlan::Tensor::kVirtual;
+      tensors[top_t[h.skipconv][0]]->kind = FusedPlan::Tensor::kVirtual;
+      tensors[top_t[h.crop][0]]->kind = FusedPlan::Tensor::kVirtual;
+      if (h.sig >= 0) tensors[top_t[h.elt][0]]->kind = FusedPlan::Tensor::kVirtual;
+      done[h.deconv] = done[h.skipconv] = done[h.crop] = done[h.elt] = 1;
+      if (h.sig >= 0) done[h.sig] = 1;
+      off += co;
+    }
+    return true;
+  }
+
+  // A convolution that will be absorbed by a head group (1x1 + bias whose output feeds a Crop reference)
+  bool IsHeadSkipConv(int i) {
+    ConvBase* c = As<ConvBase>(net.layers()[i].get());
+    if (!c->bias_term()) return false;
+    for (int cons : tensors[top_t[i][0]]->consumers)
+      if (cons >= 0 && std::string(net.layers()[cons]->type()) == "Crop") return true;
+    return false;
+  }
+
+  bool Run() {
+    BuildDataflow();
+    const int nl = static_cast<int>(net.layers().size());
+    for (int i = 0; i < nl; ++i) {
+      if (done[i]) continue;
+      const std::string type = net.layers()[i]->type();
+      if (type == "Split") { done[i] = 1; continue; }
+      if (type == "Convolution") {
+        if (IsHeadSkipConv(i)) continue;         // picked up by MatchHeads
+        if (!MatchConv(i)) return false;
+      } else if (type == "Eltwise") {
+        if (!MatchEltwise(i)) return false;
+      } else if (type == "Pooling") {
+        if (!MatchPool(i)) return false;
+      } else if (type == "Deconvolution") {
+        if (!MatchHeads(i)) return false;
+      } else {
+        return Fail("layer " + net.layer_names()[i] + " (" + type + ") is not part of a fusable pattern");
+      }
+    }
+    for (int i = 0; i < nl; ++i)
+      if (!done[i]) return Fail("layer " + net.layer_names()[i] + " was left unmatched");
+    return true;
+  }
+};
+
+size_t AlignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+FusedPlan* FusedPlan::Build(Net<float>& net, bool materialize, std::string* why_not) {
+  FusedPlan* plan = new FusedPlan();
+  plan->net_ = &net;
+  plan->materialize_ = materialize;
+  std::string why;
+  if (!plan->Match(net, materialize, &why)) {
+    if (why_not) *why_not = why;
+    delete plan;
+    return nullptr;
+  }
+  if (why_not) why_not->clear();
+  plan->PlanMemory();
+  plan->UploadWeights(net);
+  return plan;
+}
+
+bool FusedPlan::Match(Net<float>& net, bool materialize, std::string* why) {
+  Matcher m(net, tensors_, steps_);
+  if (!m.Run()) { *why = m.why; return false; }
+  // Net outputs that ended up as split activations, and (on request) every named intermediate,
+  // are converted back into their fp32 NCHW blobs.
+  std::set<int> out_blobs(net.output_blob_indices().begin(), net.output_blob_indices().end());
+  std::vector<Step*> with_copies;
+  for (Step* s : steps_) {
+    with_copies.push_back(s);
+    Tensor* t = s->out;
+    if (t && t->kind == Tensor::kSplit && t->blob >= 0 && (materialize || out_blobs.count(t->blob))) {
+      Step* c = new Step();
+      c->type = Step::kToBlob;
+      c->name = net.blob_names()[t->blob] + "/to_blob";
+      c->in = t;
+      c->out_blob = t->blob;
+      with_copies.push_back(c);
+    }
+  }
+  steps_.swap(with_copies);
+  if (materialize)
+    for (size_t i = 0; i < net.layers().size(); ++i)
+      if (std::string(net.layers()[i]->type()) == "Split") split_layers_.push_back(static_cast<int>(i));
+  return true;
+}
+
+// Liveness-based placement of every arena tensor (first-fit over a sorted free list).
+void FusedPlan::PlanMemory() {
+  for (size_t s = 0; s < steps_.size(); ++s) {
+    Step* st = steps_[s];
+    Tensor* ins[3] = {st->in, st->in2, st->col};
+    for (Tensor* t : ins)
+      if (t) t->last_step = std::max(t->last_step, static_cast<int>(s));
+    if (st->out && st->out->def_step < 0) {
+      st->out->def_step = static_cast<int>(s);
+      st->out->last_step = std::max(st->out->last_step, static_cast<int>(s));
+    }
+  }
+  struct Free { size_t off, size; };
+  std::vector<Free> free_list;
+  size_t top = 0;
+  auto alloc = [&](size_t bytes) {
+    bytes = AlignUp(bytes, 1024);
+    for (size_t i = 0; i < free_list.size(); ++i) {
+      if (free_list[i].size >= bytes) {
+        const size_t off = free_list[i].off;
+        free_list[i].off += bytes;
+        free_list[i].size -= bytes;
+        if (free_list[i].size == 0) free_list.erase(free_list.begin() + i);
+        return off;
+      }
+    }
+    // grow: extend a trailing free block if there is one
+    if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
+      const size_t off = free_list.back().off;
+      top = off + bytes;
+      free_list.pop_back();
+      return off;
+    }
+    const size_t off = top;
+    top += bytes;
+    return off;
+  };
+  auto release = [&](size_t off, size_t bytes) {
+    bytes = AlignUp(bytes, 1024);
+    Free f = {off, bytes};
+    auto it = std::lower_bound(free_list.begin(), free_list.end(), f, [](const Free& a, const Free& b) { return a.off < b.off; });
+    it = free_list.insert(it, f);
+    const size_t i = it - free_list.begin();
+    if (i + 1 < free_list.size() && free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+      free_list[i].size += free_list[i + 1].size;
+      free_list.erase(free_list.begin() + i + 1);
+    }
+    if (i > 0 && free_list[i - 1].off + free_list[i - 1].size == free_list[i].off) {
+      free_list[i - 1].size += free_list[i].size;
+      free_list.erase(free_list.begin() + i);
+    }
+  };
+  for (size_t s = 0; s < steps_.size(); ++s) {
+    Tensor* t = steps_[s]->out;
+    if (t && t->def_step == static_cast<int>(s) && (t->kind == Tensor::kSplit || t->kind == Tensor::kF32Rows)) {
+      t->bytes = t->kind == Tensor::kSplit ? t->elems() * 4 : static_cast<size_t>(t->n) * t->h * t->w * t->ld * 4;
+      t->offset = alloc(t->bytes);
+    }
+    for (Tensor* u : tensors_)
+      if (u->bytes && u->last_step == static_cast<int>(s)) release(u->offset, u->bytes);
+  }
+  arena_bytes_ = std::max<size_t>(top, 1024);
+  DC_CHECK(dc_malloc(&arena_, arena_bytes_));
+  for (Tensor* t : tensors_)
+    if (t->bytes) t->ptr = static_cast<char*>(arena_) + t->offset;
+}
+
+bool FusedPlan::WeightsStale() const {
+  for (const auto& we : weight_epochs_)
+    if (we.first->host_write_epoch() != we.second) return true;
+  return false;
+}
+
+void FusedPlan::UploadWeights(Net<float>& net) {
+  void* stream = Caffe::stream();
+  for (const auto& layer : net.layers())
+    for (const auto& blob : layer->blobs()) {
+      blob->cpu_data();     // make sure the SyncedMemory exists and is host-readable
+      weight_epochs_.push_back(std::make_pair(blob->data().get(), blob->data()->host_write_epoch()));
+    }
+  auto upload = [&](const void* host, size_t bytes) {
+    void* d = nullptr;
+    DC_CHECK(dc_malloc(&d, bytes));
+    weight_allocs_.push_back(d);
+    weight_bytes_ += bytes;
+    DC_CHECK(dc_memcpy_async(d, host, bytes, DC_H2D, stream));
+    DC_CHECK(dc_stream_sync(stream));      // the host staging buffer is reused right after
+    return d;
+  };
+  // per-channel affine of an optional BatchNorm + Scale pair
+  auto fold = [&](int bn_layer, int scale_layer, int channels, std::vector<float>* a, std::vector<float>* b) {
+    a->assign(channels, 1.f);
+    b->assign(channels, 0.f);
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    if (scale_layer >= 0) {
+      Layer<float>* sl = net.layers()[scale_layer].get();
+      gamma = sl->blobs()[0]->cpu_data();
+      if (sl->blobs().size() > 1) beta = sl->blobs()[1]->cpu_data();
+    }
+    if (bn_layer >= 0) {
+      BatchNormLayer<float>* bl = As<BatchNormLayer<float> >(net.layers()[bn_layer].get());
+      DC_CHECK(dc_fold_bn_scale(bl->blobs()[0]->cpu_data(), bl->blobs()[1]->cpu_data(), bl->blobs()[2]->cpu_data()[0], bl->eps(), gamma, beta,
+                                channels, a->data(), b->data()));
+    } else if (gamma) {
+      for (int c = 0; c < channels; ++c) { (*a)[c] = gamma[c]; (*b)[c] = beta ? beta[c] : 0.f; }
+    }
+  };
+  for (Step* st : steps_) {
+    if (st->type == Step::kConv1) {
+      Layer<float>* cl = net.layers()[st->conv_layer].get();
+      std::vector<float> wp(147 * 64), a, b;
+      DC_CHECK(dc_pack_conv1_weight(cl->blobs()[0]->cpu_data(), wp.data()));
+      fold(st->bn_layer, st->scale_layer, 64, &a, &b);
+      st->w_dev = upload(wp.data(), wp.size() * 4);
+      st->scale_dev = static_cast<float*>(upload(a.data(), 64 * 4));
+      st->shift_dev = static_cast<float*>(upload(b.data(), 64 * 4));
+    } else if (st->type == Step::kConvBN) {
+      ConvBase* cl = As<ConvBase>(net.layers()[st->conv_layer].get());
+      const int cout = st->cout, cin = cl->channels(), rows = dc_packed_rows(cout);
+      const size_t K = static_cast<size_t>(st->kh) * st->kw * cin;
+      std::vector<uint16_t> packed(2 * rows * K);
+      std::vector<float> rs(rows), a, b, scale(rows, 1.f), shift(rows, 0.f);
+      DC_CHECK(dc_pack_conv_weight(cl->blobs()[0]->cpu_data(), cout, cin, st->kh, st->kw, packed.data(), rs.data()));
+      fold(st->bn_layer, st->scale_layer, cout, &a, &b);
+      for (int c = 0; c < cout; ++c) {
+        scale[c] = a[c] * rs[c];
+        shift[c] = b[c] + (cl->bias_term() ? cl->blobs()[1]->cpu_data()[c] : 0.f);
+      }
+      st->w_dev = upload(packed.data(), packed.size() * 2);
+      st->scale_dev = static_cast<float*>(upload(scale.data(), rows * 4));
+      st->shift_dev = static_cast<float*>(upload(shift.data(), rows * 4));
+    } else if (st->type == Step::kHeadGemm) {
+      // concatenate the heads' weight blobs along the output-channel axis, then pack once
+      const int cin = st->in->c;
+      int ctot = 0;
+      for (int l : st->merged_layers) ctot += As<ConvBase>(net.layers()[l].get())->num_output();
+      const int taps = st->deconv_rows ? 9 : 1;
+      std::vector<float> wcat(static_cast<size_t>(cin) * ctot * taps);
+      std::vector<float> bias(ctot, 0.f);
+      int off = 0;
+      for (int l : st->merged_layers) {
+        ConvBase* cl = As<ConvBase>(net.layers()[l].get());
+        const int co = cl->num_output();
+        const float* w = cl->blobs()[0]->cpu_data();
+        if (st->deconv_rows) {       // W[ci][co][3][3] -> Wcat[ci][off+co][3][3]
+          for (int ci = 0; ci < cin; ++ci)
+            memcpy(&wcat[(static_cast<size_t>(ci) * ctot + off) * 9], w + static_cast<size_t>(ci) * co * 9, sizeof(float) * co * 9);
+        } else {                      // W[co][ci] -> Wcat[off+co][ci]
+          memcpy(&wcat[static_cast<size_t>(off) * cin], w, sizeof(float) * co * cin);
+        }
+        if (cl->bias_term())
+          for (int c = 0; c < co; ++c) bias[off + c] = cl->blobs()[1]->cpu_data()[c];
+        off += co;
+      }
+      const int rows = dc_packed_rows(ctot * taps);
+      std::vector<uint16_t> packed(2 * static_cast<size_t>(rows) * cin);
+      std::vector<float> rs(rows), shift(rows, 0.f);
+      if (st->deconv_rows) DC_CHECK(dc_pack_deconv_weight(wcat.data(), cin, ctot, 3, 3, packed.data(), rs.data()));
+      else DC_CHECK(dc_pack_conv_weight(wcat.data(), ctot, cin, 1, 1, packed.data(), rs.data()));
+      st->w_dev = upload(packed.data(), packed.size() * 2);
+      st->scale_dev = static_cast<float*>(upload(rs.data(), rows * 4));
+      if (!st->deconv_rows) {
+        // both biases of a head land on the same output element: fold the deconvolution's into the
+        // skip GEMM's shift (the deconv GEMM step precedes this one and recorded its biases there)
+        for (int c = 0; c < ctot; ++c) shift[c] = bias[c];
+        for (Step* other : steps_)
+          if (other->type == Step::kHeadGemm && other->deconv_rows) {
+            int o2 = 0;
+            for (int l : other->merged_layers) {
+              ConvBase* dl = As<ConvBase>(net.layers()[l].get());
+              if (dl->bias_term())
+                for (int c = 0; c < dl->num_output(); ++c) shift[o2 + c] += dl->blobs()[1]->cpu_data()[c];
+              o2 += dl->num_output();
+            }
+          }
+      }
+      st->shift_dev = static_cast<float*>(upload(shift.data(), rows * 4));
+    }
+  }
+}
+
+void FusedPlan::Run() {
+  Net<float>& net = *net_;
+  void* stream = Caffe::stream();
+  auto blob_in = [&](Tensor* t) { return net.blobs()[t->blob]->gpu_data(); };
+  for (Step* st : steps_) {
+    switch (st->type) {
+      case Step::kConv1: {
+        DC_CHECK(dc_conv1_forward(blob_in(st->in), st->in->n, st->in->h, st->in->w, static_cast<const float*>(st->w_dev), st->scale_dev,
+                                  st->shift_dev, st->out->ptr, stream));
+        break;
+      }
+      case Step::kConvBN:
+      case Step::kHeadGemm: {
+        dc_conv_args a;
+        memset(&a, 0, sizeof(a));
+        a.x = st->in->ptr; a.n = st->in->n; a.h = st->in->h; a.w = st->in->w; a.cin = st->in->c;
+        a.cout = st->cout; a.kh = st->kh; a.kw = st->kw; a.pad = st->pad; a.dilation = st->dil;
+        a.w_packed = st->w_dev; a.scale = st->scale_dev; a.shift = st->shift_dev;
+        a.residual = st->in2 && st->type == Step::kConvBN ? st->in2->ptr : nullptr;
+        a.relu = st->relu;
+        a.out_f32_rows = st->type == Step::kHeadGemm;
+        a.ldc = st->out->ld;
+        a.out = st->out->ptr;
+        DC_CHECK(dc_conv_forward(&a, stream));
+        break;
+      }
+      case Step::kSubsample:
+        DC_CHECK(dc_subsample_forward(st->in->ptr, st->in->n, st->in->h, st->in->w, st->in->c, st->stride, st->out->ptr, stream));
+        break;
+      case Step::kMaxPool:
+        DC_CHECK(dc_maxpool_forward(st->in->ptr, st->in->n, st->in->h, st->in->w, st->in->c, st->pool_k, st->pool_s, st->out->ptr, stream));
+        break;
+      case Step::kHeadFinish: {
+        Blob<float>* ob = net.blobs()[st->out_blob].get();
+        DC_CHECK(dc_head_finish(static_cast<const float*>(st->col->ptr), st->col->ld, st->col_off, static_cast<const float*>(st->in2->ptr),
+                                st->in2->ld, st->skip_off, ob->mutable_gpu_data(), st->in->n, st->cout, st->in->h, st->in->w, ob->height(),
+                                ob->width(), st->sigmoid, stream));
+        break;
+      }
+      case Step::kToBlob: {
+        Blob<float>* ob = net.blobs()[st->out_blob].get();
+        DC_CHECK(dc_split_to_nchw(st->in->ptr, st->in->n, st->in->c, st->in->h, st->in->w, ob->mutable_gpu_data(), stream));
+        break;
+      }
+    }
+  }
+  for (int l : split_layers_) net.layers()[l]->Forward(net.bottom_vecs()[l], net.top_vecs()[l]);
+}
+
+std::string FusedPlan::Describe() const {
+  std::ostringstream s;
+  static const char* kNames[] = {"Conv1", "ConvBN", "Subsample", "MaxPool", "HeadGemm", "HeadFinish", "ToBlob"};
+  s << steps_.size() << " steps, arena " << (arena_bytes_ >> 20) << " MiB, weights " << (weight_bytes_ >> 20) << " MiB\n";
+  for (const Step* st : steps_) {
+    s << "  " << kNames[st->type] << " " << st->name;
+    if (st->in) s << " in=" << st->in->n << "x" << st->in->c << "x" << st->in->h << "x" << st->in->w;
+    if (st->type == Step::kConvBN) s << " k" << st->kh << " p" << st->pad << " d" << st->dil << " ->" << st->cout << (st->relu ? " relu" : "") << (st->in2 ? " +res" : "");
+    s << "\n";
+  }
+  return s.str();
+}
+
+}  // namespace caffe

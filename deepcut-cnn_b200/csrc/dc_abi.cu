@@ -12,6 +12,7 @@
 #include "../../include/deepcut_b200.h"
 #include "conv_igemm.cuh"
 #include "hbm_kernels.cuh"
+#include "layer_kernels.cuh"
 
 namespace {
 
@@ -106,7 +107,7 @@ void pack_row(int K, Get get, uint16_t* hi, uint16_t* lo, float* rowscale) {
   *rowscale = 1.f / s;
 }
 
-int tile_n_for(int cout) { return cout >= 256 ? 256 : (cout > 64 ? 128 : 64); }
+int tile_n_for(int cout) { return cout > 64 ? 128 : 64; }
 
 int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw, int th) {
   const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, 2};
@@ -185,11 +186,77 @@ int dc_init(int device) {
     if (!fn || q != cudaDriverEntryPointSuccess) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<256>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::kC1SmemFloats * 4));
   g_inited = true;
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------ memory / streams / events
+int dc_malloc(void** ptr, size_t bytes) {
+  if (int rc = ensure_init()) return rc;
+  if (!ptr) return fail(DC_ERR_INVALID, "dc_malloc: null");
+  DC_CUDA(cudaMalloc(ptr, bytes));
+  return DC_OK;
+}
+int dc_free(void* ptr) { if (ptr) DC_CUDA(cudaFree(ptr)); return DC_OK; }
+int dc_malloc_host(void** ptr, size_t bytes) {
+  if (int rc = ensure_init()) return rc;
+  if (!ptr) return fail(DC_ERR_INVALID, "dc_malloc_host: null");
+  DC_CUDA(cudaMallocHost(ptr, bytes));
+  return DC_OK;
+}
+int dc_free_host(void* ptr) { if (ptr) DC_CUDA(cudaFreeHost(ptr)); return DC_OK; }
+int dc_memcpy_async(void* dst, const void* src, size_t bytes, int kind, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  cudaMemcpyKind k;
+  switch (kind) {
+    case DC_H2D: k = cudaMemcpyHostToDevice; break;
+    case DC_D2H: k = cudaMemcpyDeviceToHost; break;
+    case DC_D2D: k = cudaMemcpyDeviceToDevice; break;
+    default: return fail(DC_ERR_INVALID, "dc_memcpy_async: bad kind %d", kind);
+  }
+  if (bytes == 0) return DC_OK;
+  DC_CUDA(cudaMemcpyAsync(dst, src, bytes, k, static_cast<cudaStream_t>(stream)));
+  return DC_OK;
+}
+int dc_memset_async(void* ptr, int value, size_t bytes, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (bytes == 0) return DC_OK;
+  DC_CUDA(cudaMemsetAsync(ptr, value, bytes, static_cast<cudaStream_t>(stream)));
+  return DC_OK;
+}
+int dc_stream_create(void** stream) {
+  if (int rc = ensure_init()) return rc;
+  cudaStream_t s;
+  DC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = s;
+  return DC_OK;
+}
+int dc_stream_destroy(void* stream) { if (stream) DC_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(stream))); return DC_OK; }
+int dc_stream_sync(void* stream) { DC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); return DC_OK; }
+int dc_device_sync(void) { if (int rc = ensure_init()) return rc; DC_CUDA(cudaDeviceSynchronize()); return DC_OK; }
+int dc_mem_info(size_t* free_bytes, size_t* total_bytes) {
+  if (int rc = ensure_init()) return rc;
+  DC_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  return DC_OK;
+}
+int dc_event_create(void** event) {
+  if (int rc = ensure_init()) return rc;
+  cudaEvent_t e;
+  DC_CUDA(cudaEventCreate(&e));
+  *event = e;
+  return DC_OK;
+}
+int dc_event_destroy(void* event) { if (event) DC_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event))); return DC_OK; }
+int dc_event_record(void* event, void* stream) {
+  DC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
+  return DC_OK;
+}
+int dc_event_elapsed_ms(void* start, void* stop, float* ms) {
+  DC_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+  DC_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
   return DC_OK;
 }
 
@@ -327,11 +394,8 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH)) return rc;
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, bn)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 256: return launch_conv<256>(ta, tb, p, st);
-    case 128: return launch_conv<128>(ta, tb, p, st);
-    default: return launch_conv<64>(ta, tb, p, st);
-  }
+  if (bn == 128) return launch_conv<128>(ta, tb, p, st);
+  return launch_conv<64>(ta, tb, p, st);
 }
 
 // ------------------------------------------------------------------ HBM kernels
@@ -406,6 +470,57 @@ int dc_split_to_nchw(const void* x, int n, int c, int h, int w, float* out, void
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
+}
+
+// ------------------------------------------------------------------ per-layer NCHW kernels
+#define DC_EW_LAUNCH(kernel, total, ...)                                                        \
+  do {                                                                                          \
+    if (int rc = ensure_init()) return rc;                                                      \
+    if ((total) > 0) {                                                                          \
+      kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(__VA_ARGS__);       \
+      g_launches++;                                                                             \
+      DC_CUDA(cudaGetLastError());                                                              \
+    }                                                                                           \
+    return DC_OK;                                                                               \
+  } while (0)
+
+int dc_bn_forward_nchw(const float* x, const float* mean, const float* stddev, int n, int c, int hw, float* y, void* stream) {
+  const long long total = static_cast<long long>(n) * c * hw;
+  DC_EW_LAUNCH(dc::bn_nchw_kernel, total, x, mean, stddev, total, c, hw, y);
+}
+int dc_scale_forward_nchw(const float* x, const float* gamma, const float* beta, int n, int c, int hw, float* y, void* stream) {
+  const long long total = static_cast<long long>(n) * c * hw;
+  DC_EW_LAUNCH(dc::scale_nchw_kernel, total, x, gamma, beta, total, c, hw, y);
+}
+int dc_relu_forward(const float* x, long long count, float negative_slope, float* y, void* stream) {
+  DC_EW_LAUNCH(dc::relu_kernel, count, x, count, negative_slope, y);
+}
+int dc_sigmoid_forward(const float* x, long long count, float* y, void* stream) {
+  DC_EW_LAUNCH(dc::sigmoid_kernel, count, x, count, y);
+}
+int dc_axpby_forward(const float* a, float ca, const float* b, float cb, long long count, float* y, void* stream) {
+  DC_EW_LAUNCH(dc::axpby_kernel, count, a, ca, b, cb, count, y);
+}
+int dc_crop_forward_nchw(const float* x, int n, int c, int h, int w, int off_h, int off_w, int ho, int wo, float* y, void* stream) {
+  const long long total = static_cast<long long>(n) * c * ho * wo;
+  DC_EW_LAUNCH(dc::crop_nchw_kernel, total, x, h, w, off_h, off_w, ho, wo, total, y);
+}
+int dc_maxpool_forward_nchw(const float* x, int n, int c, int h, int w, int kh, int kw, int sh, int sw, int ph, int pw,
+                            int ho, int wo, float* y, void* stream) {
+  const long long total = static_cast<long long>(n) * c * ho * wo;
+  DC_EW_LAUNCH(dc::maxpool_nchw_kernel, total, x, h, w, kh, kw, sh, sw, ph, pw, ho, wo, total, y);
+}
+int dc_conv_direct_nchw(const float* x, const float* w, const float* bias, int n, int cin, int h, int wd, int cout,
+                        int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, float* y, void* stream) {
+  const int ho = (h + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1, wo = (wd + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+  const long long total = static_cast<long long>(n) * cout * ho * wo;
+  DC_EW_LAUNCH(dc::conv_direct_nchw_kernel, total, x, w, bias, cin, h, wd, cout, kh, kw, sh, sw, ph, pw, dh, dw, ho, wo, total, y);
+}
+int dc_deconv_direct_nchw(const float* x, const float* w, const float* bias, int n, int cin, int h, int wd, int cout,
+                          int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, float* y, void* stream) {
+  const int ho = sh * (h - 1) + dh * (kh - 1) + 1 - 2 * ph, wo = sw * (wd - 1) + dw * (kw - 1) + 1 - 2 * pw;
+  const long long total = static_cast<long long>(n) * cout * ho * wo;
+  DC_EW_LAUNCH(dc::deconv_direct_nchw_kernel, total, x, w, bias, cin, h, wd, cout, kh, kw, sh, sw, ph, pw, dh, dw, ho, wo, total, y);
 }
 
 }  // extern "C"

@@ -20,6 +20,21 @@ _SIGS = {
     "dc_device_count": (C.c_int, []),
     "dc_init": (C.c_int, [C.c_int]),
     "dc_launch_count": (C.c_longlong, []),
+    "dc_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "dc_free": (C.c_int, [C.c_void_p]),
+    "dc_malloc_host": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "dc_free_host": (C.c_int, [C.c_void_p]),
+    "dc_memcpy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "dc_memset_async": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "dc_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "dc_stream_destroy": (C.c_int, [C.c_void_p]),
+    "dc_stream_sync": (C.c_int, [C.c_void_p]),
+    "dc_device_sync": (C.c_int, []),
+    "dc_mem_info": (C.c_int, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "dc_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "dc_event_destroy": (C.c_int, [C.c_void_p]),
+    "dc_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dc_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "dc_fold_bn_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p]),
     "dc_packed_rows": (C.c_int, [C.c_int]),
@@ -39,6 +54,15 @@ _SIGS = {
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dc_nchw_to_split": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dc_split_to_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dc_bn_forward_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dc_scale_forward_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dc_relu_forward": (C.c_int, [C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p]),
+    "dc_sigmoid_forward": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "dc_axpby_forward": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "dc_crop_forward_nchw": (C.c_int, [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
+    "dc_maxpool_forward_nchw": (C.c_int, [C.c_void_p] + [C.c_int] * 12 + [C.c_void_p, C.c_void_p]),
+    "dc_conv_direct_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 13 + [C.c_void_p, C.c_void_p]),
+    "dc_deconv_direct_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 13 + [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

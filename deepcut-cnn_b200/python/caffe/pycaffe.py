@@ -1,0 +1,235 @@
+"""Net / Blob / Layer with the pycaffe surface (reference python/caffe/pycaffe.py:22-108,
+_caffe.cpp:225-276): OrderedDict views `blobs` and `params`, `inputs`/`outputs`, `forward(**kwargs)`,
+`Blob.data` as a zero-copy NumPy view of mutable_cpu_data() that keeps the blob alive."""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _caffe
+from ._caffe import lib, check, check_ptr
+
+
+class Blob(object):
+    def __init__(self, handle, owner=None):
+        self._h = handle
+        self._owner = owner        # keeps the Net python object alive for name tables only
+
+    def __del__(self):
+        try:
+            lib.caffe_blob_release(self._h)
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return tuple(lib.caffe_blob_shape(self._h, i) for i in range(lib.caffe_blob_num_axes(self._h)))
+
+    @property
+    def count(self):
+        return lib.caffe_blob_count(self._h)
+
+    def _legacy(self, i):
+        s = self.shape
+        return s[i] if i < len(s) else 1
+
+    num = property(lambda self: self._legacy(0))
+    channels = property(lambda self: self._legacy(1))
+    height = property(lambda self: self._legacy(2))
+    width = property(lambda self: self._legacy(3))
+
+    def reshape(self, *dims):
+        if len(dims) == 1 and isinstance(dims[0], (tuple, list)):
+            dims = tuple(dims[0])
+        arr = (C.c_int * len(dims))(*[int(d) for d in dims])
+        check(lib.caffe_blob_reshape(self._h, len(dims), arr))
+
+    def _view(self, ptr):
+        shape = self.shape
+        n = int(np.prod(shape)) if shape else 0
+        if n == 0:
+            return np.zeros(shape, np.float32)
+        buf = (C.c_float * n).from_address(check_ptr(ptr))
+        a = np.frombuffer(buf, dtype=np.float32).reshape(shape)
+        a.flags.writeable = True
+        self._keep = buf
+        # the array holds a reference to this Blob object, which holds the shared_ptr handle
+        return _BlobArray(a, self)
+
+    @property
+    def data(self):
+        return self._view(lib.caffe_blob_mutable_cpu_data(self._h))
+
+    @property
+    def diff(self):
+        return self._view(lib.caffe_blob_mutable_cpu_diff(self._h))
+
+    def gpu_data_ptr(self):
+        return check_ptr(lib.caffe_blob_gpu_data(self._h))
+
+
+class _BlobArray(np.ndarray):
+    """ndarray view that keeps its Blob (hence the C++ shared_ptr) alive."""
+    def __new__(cls, arr, blob):
+        obj = arr.view(cls)
+        obj._blob = blob
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._blob = getattr(obj, "_blob", None)
+
+
+class Layer(object):
+    def __init__(self, net, index):
+        self._net = net
+        self._i = index
+        self.type = lib.caffe_net_layer_type(net._h, index).decode()
+        self.blobs = [Blob(check_ptr(lib.caffe_net_layer_blob(net._h, index, j)))
+                      for j in range(lib.caffe_net_layer_num_blobs(net._h, index))]
+
+
+class Net(object):
+    def __init__(self, network_file, *args, **kwargs):
+        """Net(network_file, phase) | Net(network_file, weights_file, phase) -- the two ctor forms
+        of the reference binding (_caffe.cpp:76-96)."""
+        weights = kwargs.get("weights")
+        phase = kwargs.get("phase")
+        if len(args) == 1:
+            phase = args[0]
+        elif len(args) == 2:
+            weights, phase = args
+        if phase is None:
+            raise TypeError("Net(network_file, [weights_file,] phase)")
+        with open(network_file):          # same failure mode as CheckFile (_caffe.cpp:45-52)
+            pass
+        self._h = check_ptr(lib.caffe_net_create(network_file.encode(), int(phase)))
+        if weights is not None:
+            with open(weights):
+                pass
+            check(lib.caffe_net_copy_trained_from(self._h, weights.encode()))
+        self._build_tables()
+
+    @classmethod
+    def from_string(cls, prototxt_text, phase):
+        self = cls.__new__(cls)
+        self._h = check_ptr(lib.caffe_net_create_from_string(prototxt_text.encode(), int(phase)))
+        self._build_tables()
+        return self
+
+    def _build_tables(self):
+        h = self._h
+        self._blob_names = [lib.caffe_net_blob_name(h, i).decode() for i in range(lib.caffe_net_num_blobs(h))]
+        self._layer_names = [lib.caffe_net_layer_name(h, i).decode() for i in range(lib.caffe_net_num_layers(h))]
+        self._blobs = [Blob(check_ptr(lib.caffe_net_blob(h, i))) for i in range(len(self._blob_names))]
+        self.layers = [Layer(self, i) for i in range(len(self._layer_names))]
+        self._inputs = [lib.caffe_net_input_index(h, i) for i in range(lib.caffe_net_num_inputs(h))]
+        self._outputs = [lib.caffe_net_output_index(h, i) for i in range(lib.caffe_net_num_outputs(h))]
+
+    def __del__(self):
+        try:
+            lib.caffe_net_destroy(self._h)
+        except Exception:
+            pass
+
+    # ---- pycaffe views (pycaffe.py:22-60)
+    @property
+    def blobs(self):
+        return OrderedDict(zip(self._blob_names, self._blobs))
+
+    @property
+    def params(self):
+        return OrderedDict((name, lr.blobs) for name, lr in zip(self._layer_names, self.layers) if len(lr.blobs) > 0)
+
+    @property
+    def inputs(self):
+        return [self._blob_names[i] for i in self._inputs]
+
+    @property
+    def outputs(self):
+        return [self._blob_names[i] for i in self._outputs]
+
+    @property
+    def name(self):
+        return lib.caffe_net_name(self._h).decode()
+
+    def bottom_names(self, layer_index):
+        h = self._h
+        return [self._blob_names[lib.caffe_net_layer_bottom_id(h, layer_index, j)]
+                for j in range(lib.caffe_net_layer_num_bottoms(h, layer_index))]
+
+    def top_names(self, layer_index):
+        h = self._h
+        return [self._blob_names[lib.caffe_net_layer_top_id(h, layer_index, j)]
+                for j in range(lib.caffe_net_layer_num_tops(h, layer_index))]
+
+    # ---- execution
+    def _forward(self, start, end):
+        check(lib.caffe_net_forward_from_to(self._h, start, end))
+
+    def forward(self, blobs=None, start=None, end=None, **kwargs):
+        """pycaffe.py:62-108: copy kwargs into input blobs, run, return {output name: array}."""
+        if blobs is None:
+            blobs = []
+        if kwargs:
+            if set(kwargs.keys()) != set(self.inputs):
+                raise Exception("Input blob arguments do not match net inputs.")
+            for in_, blob in kwargs.items():
+                if blob.shape[0] != self.blobs[in_].num:
+                    raise Exception("Input is not batch sized")
+                self.blobs[in_].data[...] = blob
+        if start is None and end is None:
+            check(lib.caffe_net_forward(self._h))
+            outputs = set(self.outputs + blobs)
+        else:
+            start_ind = 0 if start is None else self._layer_names.index(start)
+            if end is None:
+                end_ind = len(self.layers) - 1
+                outputs = set(self.outputs + blobs)
+            else:
+                end_ind = self._layer_names.index(end)
+                outputs = set([end] + blobs)
+            self._forward(start_ind, end_ind)
+        return {out: self.blobs[out].data for out in outputs}
+
+    def reshape(self):
+        check(lib.caffe_net_reshape(self._h))
+
+    def copy_from(self, weights_file):
+        with open(weights_file):
+            pass
+        check(lib.caffe_net_copy_trained_from(self._h, weights_file.encode()))
+
+    def save(self, filename):
+        check(lib.caffe_net_save(self._h, filename.encode()))
+
+    # ---- B200 extensions
+    def set_fusion(self, on):
+        check(lib.caffe_net_set_fusion(self._h, int(bool(on))))
+
+    def materialize_intermediates(self, on):
+        check(lib.caffe_net_materialize_intermediates(self._h, int(bool(on))))
+
+    @property
+    def fused_last_forward(self):
+        return bool(lib.caffe_net_fused_last_forward(self._h))
+
+    @property
+    def fusion_diagnostic(self):
+        return lib.caffe_net_fusion_diagnostic(self._h).decode()
+
+    @property
+    def last_forward_launches(self):
+        return lib.caffe_net_last_forward_launches(self._h)
+
+    def set_params(self, weights):
+        """weights: {layer name: [arrays]} written through the param views (harness helper)."""
+        params = self.params
+        for name, arrs in weights.items():
+            if name not in params:
+                raise KeyError("net has no parameterised layer '%s'" % name)
+            if len(arrs) != len(params[name]):
+                raise ValueError("layer %s: %d blobs given, %d expected" % (name, len(arrs), len(params[name])))
+            for blob, a in zip(params[name], arrs):
+                if tuple(blob.shape) != tuple(a.shape):
+                    raise ValueError("layer %s: shape %s given, %s expected" % (name, a.shape, blob.shape))
+                blob.data[...] = a

@@ -42,6 +42,30 @@ int dc_init(int device);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 long long dc_launch_count(void);
 
+/* ---- device memory / streams (what SyncedMemory and the activation arena sit on) ------ */
+/* Replaces the cudaMalloc / cudaMallocHost / cudaMemcpy calls of SyncedMemory
+ * (src/caffe/syncedmem.cpp:7-77, include/caffe/syncedmem.hpp:15-36) and caffe_gpu_memcpy
+ * (src/caffe/util/math_functions.cu:77-81).  Copies are asynchronous on `stream`. */
+#define DC_H2D 1
+#define DC_D2H 2
+#define DC_D2D 3
+int dc_malloc(void** ptr, size_t bytes);
+int dc_free(void* ptr);
+int dc_malloc_host(void** ptr, size_t bytes);      /* pinned */
+int dc_free_host(void* ptr);
+int dc_memcpy_async(void* dst, const void* src, size_t bytes, int kind, void* stream);
+int dc_memset_async(void* ptr, int value, size_t bytes, void* stream);
+int dc_stream_create(void** stream);
+int dc_stream_destroy(void* stream);
+int dc_stream_sync(void* stream);
+int dc_device_sync(void);
+int dc_mem_info(size_t* free_bytes, size_t* total_bytes);
+/* Timing with CUDA events on `stream` (Timer, src/caffe/util/benchmark.cpp:8-118). */
+int dc_event_create(void** event);
+int dc_event_destroy(void* event);
+int dc_event_record(void* event, void* stream);
+int dc_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
+
 /* ---- load-time weight transforms (host side, no GPU needed) ------------------------- */
 /* y = (x - mean*sf) / sqrt(var*sf + eps) * gamma + beta  ==  a*x + b with sf = (factor==0 ? 0 : 1/factor)
  * BatchNormLayer inference branch (src/caffe/layers/batch_norm_layer.cpp:86-93,137-149) folded with
@@ -57,7 +81,7 @@ int dc_tile_n(int cout);
  * K-major split-fp16 matrix the implicit GEMM reads: packed[2][rows][K], K = (p*kw+q)*cin + ci,
  * rows = dc_packed_rows(cout) (zero padded).  Each row is multiplied by a power of two so its
  * largest |w| lands in [2^9, 2^10) (keeps the lo plane out of fp16 subnormals); rowscale[r]
- * receives the exact inverse (0 for padding rows... 1 is stored so products stay finite). */
+ * receives the exact inverse (1 for the zero padding rows). */
 int dc_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, uint16_t* packed, float* rowscale);
 /* Same for a Deconvolution blob W[cin][cout][kh][kw] (reverse_dimensions, base_conv_layer.cpp:125-131):
  * GEMM row = co*kh*kw + p*kw + q, K = ci; rows = dc_packed_rows(cout*kh*kw). */
@@ -109,6 +133,29 @@ int dc_head_finish(const float* col, int ldcol, int col_off, const float* skip, 
 /* Blob materialisation: fp32 NCHW <-> split NHWC. */
 int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream);
 int dc_split_to_nchw(const void* x, int n, int c, int h, int w, float* out, void* stream);
+
+
+/* ---- per-layer fp32 NCHW kernels (Layer::Forward_gpu, one layer at a time) -------------- */
+/* (x - mean[c]) / std[c]: BatchNormLayer::Forward_gpu inference branch, batch_norm_layer.cu:22-89 */
+int dc_bn_forward_nchw(const float* x, const float* mean, const float* stddev, int n, int c, int hw, float* y, void* stream);
+/* x * gamma[c] (+ beta[c]): ScaleLayer::Forward_gpu, scale_layer.cu:19-56 */
+int dc_scale_forward_nchw(const float* x, const float* gamma, const float* beta, int n, int c, int hw, float* y, void* stream);
+/* ReLULayer::Forward_gpu relu_layer.cu:8-32; SigmoidLayer::Forward_gpu sigmoid_layer.cu:8-24 */
+int dc_relu_forward(const float* x, long long count, float negative_slope, float* y, void* stream);
+int dc_sigmoid_forward(const float* x, long long count, float* y, void* stream);
+/* y = ca*a + cb*b: EltwiseLayer::Forward_gpu SUM, eltwise_layer.cu:47-53 */
+int dc_axpby_forward(const float* a, float ca, const float* b, float cb, long long count, float* y, void* stream);
+/* CropLayer::Forward_gpu crop_layer.cu:9-38 */
+int dc_crop_forward_nchw(const float* x, int n, int c, int h, int w, int off_h, int off_w, int ho, int wo, float* y, void* stream);
+/* PoolingLayer::Forward_gpu MAX pooling_layer.cu:10-47 (any kernel/stride/pad; ho/wo from the layer's Reshape) */
+int dc_maxpool_forward_nchw(const float* x, int n, int c, int h, int w, int kh, int kw, int sh, int sw, int ph, int pw,
+                            int ho, int wo, float* y, void* stream);
+/* Generic direct (de)convolution for geometries outside the tcgen05 kernel: conv_layer.cu:8-24, deconv_layer.cu:8-24.
+ * w is the Caffe blob ([cout][cin][kh][kw] for conv, [cin][cout][kh][kw] for deconv); bias may be NULL. */
+int dc_conv_direct_nchw(const float* x, const float* w, const float* bias, int n, int cin, int h, int wd, int cout,
+                        int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, float* y, void* stream);
+int dc_deconv_direct_nchw(const float* x, const float* w, const float* bias, int n, int cin, int h, int wd, int cout,
+                          int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, float* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -80,23 +80,28 @@ def sgemm(a, b):
 # --------------------------------------------------------------------------
 # layers
 # --------------------------------------------------------------------------
+def _hw(v):
+    return (v, v) if np.isscalar(v) else tuple(v)
+
+
 def convolution(x, w, b, stride, pad, dil):
     """ConvolutionLayer::Forward_cpu conv_layer.cpp:25-40 ->
     forward_cpu_gemm base_conv_layer.cpp:256-272 (im2col skipped iff 1x1/s1/p0,
-    :109-116) + forward_cpu_bias :274-280.  w: [Cout,Cin,kh,kw]."""
+    :109-116) + forward_cpu_bias :274-280.  w: [Cout,Cin,kh,kw]; stride/pad/dil: int or (h, w)."""
     N, C, H, W = x.shape
     Co, Ci, kh, kw = w.shape
     assert Ci == C, "groups unsupported (deepercut uses group=1)"
-    is_1x1 = kh == 1 and kw == 1 and stride == 1 and pad == 0
-    Ho = conv_out_size(H, kh, pad, stride, dil)
-    Wo = conv_out_size(W, kw, pad, stride, dil)
+    (sh, sw), (ph, pw), (dh, dw) = _hw(stride), _hw(pad), _hw(dil)
+    is_1x1 = kh == 1 and kw == 1 and sh == 1 and sw == 1 and ph == 0 and pw == 0
+    Ho = conv_out_size(H, kh, ph, sh, dh)
+    Wo = conv_out_size(W, kw, pw, sw, dw)
     y = np.empty((N, Co, Ho, Wo), F32)
     wm = w.reshape(Co, Ci * kh * kw)
     for n in range(N):
         if is_1x1:
             col = x[n].reshape(C, H * W)
         else:
-            col, _, _ = im2col(x[n], kh, kw, pad, pad, stride, stride, dil, dil)
+            col, _, _ = im2col(x[n], kh, kw, ph, pw, sh, sw, dh, dw)
         out = sgemm(wm, col)
         if b is not None:
             # rank-1 GEMM with the ones vector: out += b * 1^T  (beta = 1)

@@ -24,7 +24,8 @@ def _tokens(text):
             raise ValueError("prototxt: bad character at offset %d" % pos)
         pos = m.end()
         if m.lastgroup == "str":
-            out.append(("str", m.group("str")[1:-1]))
+            out.append(("str", re.sub(r"\\(.)", lambda e: {"n": "\n", "t": "\t"}.get(e.group(1), e.group(1)),
+                                      m.group("str")[1:-1])))
         elif m.lastgroup == "punct":
             out.append(("p", m.group("punct")))
         elif m.lastgroup == "word":

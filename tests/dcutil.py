@@ -65,3 +65,21 @@ def fold_bn(bn, sc, eps=1e-5):
                                    float(bn[2][0]), eps, ptr(g) if g is not None else None,
                                    ptr(be) if be is not None else None, c, ptr(a), ptr(b)))
     return a, b
+
+
+def caffe_module():
+    """The pycaffe-compatible shim over libcaffe_b200.so."""
+    import os
+    import sys
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deepcut-cnn_b200", "python")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import caffe
+    return caffe
+
+
+def write_prototxt(tmpdir, **kw):
+    import os
+    path = os.path.join(str(tmpdir), "net_%s.prototxt" % "_".join(str(v) for v in kw.values()).replace(" ", "").replace(",", "-").strip("()"))
+    gen_prototxt.write(path, **kw)
+    return path

@@ -1,0 +1,143 @@
+"""Host logic on CPU: prototxt loader, Net::Init graph (names, splits, shapes, outputs), weight
+file round trip, error behaviour.  No compute: the product has no CPU forward path."""
+import os
+
+import numpy as np
+import pytest
+
+import dcutil
+from oracle import caffe_ref, prototxt as opt
+
+caffe = dcutil.caffe_module()
+REF_PROTOTXT = "/root/reference/models/deepercut/ResNet-152.prototxt"
+
+
+def test_generated_prototxt_equals_reference_structure():
+    if not os.path.exists(REF_PROTOTXT):
+        pytest.skip("reference not mounted on this box")
+    ref = opt.parse_file(REF_PROTOTXT)
+    gen = opt.parse(dcutil.gen_prototxt.generate())
+    assert ref == gen           # name, input, input_dim and all 680 layers, field for field
+
+
+def test_both_parsers_agree():
+    txt = dcutil.gen_prototxt.generate(height=64, width=96)
+    a, b = opt.parse(txt), dcutil.ptx.parse(txt)
+    assert a == b and len(b["layer"]) == 680
+    tricky = "a { s: 'x # y' t: \"q\\\"r\" } v: [1, 2.5e-3, -7] w < k: FOO > # trailing"
+    assert opt.parse(tricky) == dcutil.ptx.parse(tricky) == {"a": [{"s": ["x # y"], "t": ['q"r']}], "v": [1, 2.5e-3, -7], "w": [{"k": ["FOO"]}]}
+
+
+def test_net_init_matches_reference_graph(tmp_path):
+    path = dcutil.write_prototxt(tmp_path, height=256, width=256)
+    net = caffe.Net(path, caffe.TEST)
+    # 680 layers + one Split per multiply-read top (insert_splits.cpp): 50 block inputs... counted by the oracle
+    onet = caffe_ref.load_net(path)
+    assert net.inputs == ["data"]
+    assert net.outputs == ["loc_pred", "next_pred", "prob"]          # std::set order, net.cpp:268-274
+    assert [n for n in net._layer_names if "_split" not in n] == [opt.get(l, "name") for l in onet.layers]
+    for name, shape in onet.blob_shapes.items():
+        assert tuple(net.blobs[name].shape) == tuple(shape), name
+    # split naming: <blob>_<last writer layer>_<top idx>_split[_k]  (insert_splits.cpp:129-143)
+    assert "pool1_pool1_0_split" in net._layer_names
+    assert "res2a_res2a_relu_0_split_1" in net._blob_names
+    assert "res3b7_res3b7_relu_0_split_4" in net._blob_names          # 5 readers: res4a x2 + 3 skip heads
+    # parameter blob orders and shapes
+    assert [tuple(b.shape) for b in net.params["bn_conv1"]] == [(64,), (64,), (1,)]
+    assert [tuple(b.shape) for b in net.params["scale_conv1"]] == [(64,), (64,)]
+    assert [tuple(b.shape) for b in net.params["res5c_up_next"]] == [(2048, 364, 3, 3), (364,)]
+    assert [tuple(b.shape) for b in net.params["res5a_branch2b"]] == [(512, 512, 3, 3)]
+    for lname, shapes in onet.param_shapes.items():
+        assert [tuple(b.shape) for b in net.params[lname]] == [tuple(s) for s in shapes], lname
+    # unloaded net: constant-0 fillers, Scale gamma defaults to 1 (scale_layer.cpp:36-40)
+    assert not net.params["conv1"][0].data.any() and np.all(net.params["scale_conv1"][0].data == 1)
+
+
+def test_reshape_propagates(tmp_path):
+    path = dcutil.write_prototxt(tmp_path, height=128, width=128)
+    net = caffe.Net(path, caffe.TEST)
+    net.blobs["data"].reshape(2, 3, 720, 1280)
+    net.reshape()
+    assert net.blobs["conv1"].shape == (2, 64, 360, 640)
+    assert net.blobs["pool1"].shape == (2, 64, 180, 320)
+    assert net.blobs["res3b7"].shape == (2, 512, 90, 160)
+    assert net.blobs["res5c"].shape == (2, 2048, 45, 80)
+    assert net.blobs["res5c_up_pose"].shape == (2, 14, 91, 161)
+    assert net.blobs["prob"].shape == (2, 14, 90, 160) and net.blobs["loc_pred"].shape == (2, 28, 90, 160)
+
+
+def test_insert_splits_known_answer():
+    # TestInsertion of the reference (src/caffe/test/test_split_layer.cpp:283-420): data feeds two
+    # inner products and a loss reads both -> one split with two outputs, consumers renamed in order.
+    src = """
+    name: "TestNetwork"
+    input: "data" input_dim: 1 input_dim: 3 input_dim: 8 input_dim: 8
+    layer { name: "c1" type: "Convolution" bottom: "data" top: "a" convolution_param { num_output: 4 kernel_size: 1 } }
+    layer { name: "c2" type: "Convolution" bottom: "data" top: "b" convolution_param { num_output: 4 kernel_size: 1 } }
+    layer { name: "r" type: "ReLU" bottom: "a" top: "a" }
+    layer { name: "s1" type: "Eltwise" bottom: "a" bottom: "b" top: "s1" }
+    layer { name: "s2" type: "Eltwise" bottom: "a" bottom: "s1" top: "s2" }
+    """
+    out = opt.parse(caffe.insert_splits_text(src))
+    names = [opt.get(l, "name") for l in out["layer"]]
+    assert names == ["data_input_0_split", "c1", "c2", "r", "a_r_0_split", "s1", "s2"]
+    L = {opt.get(l, "name"): l for l in out["layer"]}
+    assert L["data_input_0_split"]["top"] == ["data_input_0_split_0", "data_input_0_split_1"]
+    assert L["c1"]["bottom"] == ["data_input_0_split_0"] and L["c2"]["bottom"] == ["data_input_0_split_1"]
+    assert L["r"]["bottom"] == ["a"] and L["r"]["top"] == ["a"]      # in-place stays in-place
+    assert L["a_r_0_split"]["bottom"] == ["a"] and L["a_r_0_split"]["top"] == ["a_r_0_split_0", "a_r_0_split_1"]
+    assert L["s1"]["bottom"] == ["a_r_0_split_0", "b"] and L["s2"]["bottom"] == ["a_r_0_split_1", "s1"]
+
+
+def test_caffemodel_round_trip(tmp_path):
+    # python/caffe/test/test_net.py:62-81: save -> load gives identical parameters
+    path = dcutil.write_prototxt(tmp_path, stages=(1, 1, 1, 1), height=64, width=64)
+    net = caffe.Net(path, caffe.TEST)
+    rng = np.random.default_rng(0)
+    for name, blobs in net.params.items():
+        for b in blobs:
+            b.data[...] = rng.standard_normal(b.shape).astype(np.float32)
+    model = os.path.join(str(tmp_path), "w.caffemodel")
+    net.save(model)
+    net2 = caffe.Net(path, model, caffe.TEST)
+    for name in net.params:
+        for a, b in zip(net.params[name], net2.params[name]):
+            assert np.array_equal(a.data, b.data), name
+    # wire format sanity: NetParameter.layer is field 100 (tag bytes 0xa2 0x06), BlobProto.data packed floats
+    raw = open(model, "rb").read()
+    assert b"\xa2\x06" in raw[:64] and len(raw) > 4 * sum(b.count for bl in net.params.values() for b in bl)
+
+
+def test_blob_memory_outlives_net(tmp_path):
+    # python/caffe/test/test_net.py:48-60
+    path = dcutil.write_prototxt(tmp_path, stages=(1, 1, 1, 1), height=64, width=64)
+    net = caffe.Net(path, caffe.TEST)
+    params = sum(([b for b in bl] for bl in net.params.values()), [])
+    blobs = list(net.blobs.values())
+    views = [p.data for p in params[:4]] + [b.data for b in blobs[:4]]
+    for v in views:
+        v[...] = 3.0
+    del net, params, blobs
+    assert all(float(v.sum()) == 3.0 * v.size for v in views)
+
+
+def test_errors_are_exceptions_not_aborts(tmp_path):
+    with pytest.raises((IOError, OSError)):
+        caffe.Net("/nonexistent/net.prototxt", caffe.TEST)
+    bad = os.path.join(str(tmp_path), "bad.prototxt")
+    open(bad, "w").write('input: "data" input_dim: 1 input_dim: 3 input_dim: 8 input_dim: 8\n'
+                         'layer { name: "x" type: "NoSuchLayer" bottom: "data" top: "y" }')
+    with pytest.raises(caffe.CaffeError, match="Unknown layer type"):
+        caffe.Net(bad, caffe.TEST)
+    open(bad, "w").write('input: "data" input_dim: 1 input_dim: 3 input_dim: 8 input_dim: 8\n'
+                         'layer { name: "x" type: "ReLU" bottom: "nope" top: "y" }')
+    with pytest.raises(caffe.CaffeError, match="Unknown bottom blob"):
+        caffe.Net(bad, caffe.TEST)
+    path = dcutil.write_prototxt(tmp_path, stages=(1, 1, 1, 1), height=64, width=64)
+    caffe.set_mode_cpu()
+    net = caffe.Net(path, caffe.TEST)
+    with pytest.raises(caffe.CaffeError, match="no CPU forward path"):
+        net.forward()
+    with pytest.raises(Exception):
+        net.params["conv1"][0].reshape(1, 2, 3)
+        net.copy_from("/nonexistent.caffemodel")

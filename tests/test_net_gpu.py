@@ -1,0 +1,131 @@
+"""End-to-end parity (GPU): the product's Net::Forward (fused B200 plan behind the Caffe API, through
+the pycaffe-compatible shim) vs the CPU oracle on the same prototxt, inputs and weights.
+Tolerance: BASELINE.json north_star -- scoremaps within 1e-3 max-abs fp32; we hold all three
+outputs (prob, loc_pred, next_pred) to it."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import dcutil
+import netutil
+
+TOL = 1e-3
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_net.npz")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _report(tag, got, ref):
+    errs = {k: netutil.max_err(got[k], ref[k]) for k in ("prob", "loc_pred", "next_pred")}
+    print("\n[parity] %s: %s" % (tag, "  ".join("%s %.3e" % kv for kv in errs.items())))
+    return errs
+
+
+def test_tiny_net_fused_matches_oracle_and_golden(tmp_path):
+    path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
+    x = dcutil.synth.images(2, 64, 64, seed=7)
+    ref = netutil.oracle_forward(path, weights, x)
+    net = netutil.product_net(path, weights)
+    got = netutil.product_forward(net, x)
+    assert net.fused_last_forward, net.fusion_diagnostic
+    assert net.last_forward_launches > 0
+    errs = _report("tiny fused", got, ref)
+    assert max(errs.values()) < 1e-4
+    g = np.load(GOLDEN)
+    for k in ("prob", "loc_pred", "next_pred"):
+        assert netutil.max_err(got[k], g[k]) < 1e-4, k
+
+
+def test_layerwise_plugin_path_matches_oracle(tmp_path):
+    # Layer::Forward_gpu one layer at a time (the reference's plugin boundary), no fusion
+    path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
+    x = dcutil.synth.images(1, 64, 64, seed=8)
+    ref = netutil.oracle_forward(path, weights, x, want={"conv1_relu", "pool1", "res3a_relu", "res5a_branch2b_relu", "res5a_up_pose", "crop1"})
+    net = netutil.product_net(path, weights)
+    net.set_fusion(False)
+    got = netutil.product_forward(net, x)
+    assert not net.fused_last_forward
+    errs = _report("tiny layerwise", got, ref)
+    assert max(errs.values()) < 1e-4
+    # every intermediate is materialised on this path, like the reference
+    for blob, layer in (("conv1", "conv1_relu"), ("pool1", "pool1"), ("res3a", "res3a_relu"), ("res5a_branch2b", "res5a_branch2b_relu"),
+                        ("res5a_up_pose", "res5a_up_pose"), ("res5a_up_posec", "crop1")):
+        assert netutil.max_err(np.array(net.blobs[blob].data), ref[layer]) < 1e-4, blob
+    # partial forward (Net::ForwardFromTo through pycaffe's start/end)
+    out = net.forward(start="res5a_up_pose", end="prob")
+    assert netutil.max_err(out["prob"], ref["prob"]) < 1e-4
+
+
+def test_materialized_intermediates_under_fusion(tmp_path):
+    path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
+    x = dcutil.synth.images(1, 64, 64, seed=9)
+    want = {"conv1_relu": "conv1", "pool1": "pool1", "res2a_branch2a_relu": "res2a_branch2a", "res2a_relu": "res2a",
+            "res4a_relu": "res4a", "res5a_relu": "res5a"}
+    ref = netutil.oracle_forward(path, weights, x, want=set(want))
+    net = netutil.product_net(path, weights)
+    net.materialize_intermediates(True)
+    got = netutil.product_forward(net, x)
+    assert net.fused_last_forward
+    for layer, blob in want.items():
+        assert netutil.max_err(np.array(net.blobs[blob].data), ref[layer]) < 1e-4, blob
+    assert max(_report("tiny materialised", got, ref).values()) < 1e-4
+
+
+def test_reshape_and_repeat_is_bitwise_stable(tmp_path):
+    # NetTest.TestReshape (src/caffe/test/test_net.cpp:2262-2332): forward, reshape, forward, reshape back
+    path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
+    net = netutil.product_net(path, weights)
+    x1 = dcutil.synth.images(1, 64, 64, seed=1)
+    x2 = dcutil.synth.images(2, 96, 80, seed=2)
+    a = netutil.product_forward(net, x1)
+    b = netutil.product_forward(net, x2)
+    assert b["prob"].shape == (2, 14, 12, 10)
+    ref2 = netutil.oracle_forward(path, weights, x2)
+    assert max(_report("tiny 2x96x80", b, ref2).values()) < 1e-4
+    c = netutil.product_forward(net, x1)
+    for k in a:
+        assert np.array_equal(a[k], c[k]), k
+
+
+def test_host_weight_write_invalidates_packed_cache(tmp_path):
+    path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
+    net = netutil.product_net(path, weights)
+    x = dcutil.synth.images(1, 64, 64, seed=4)
+    a = netutil.product_forward(net, x)
+    w2 = {k: [np.array(v) for v in vs] for k, vs in weights.items()}
+    w2["res5a_up_pose"][1] = w2["res5a_up_pose"][1] + 0.5         # deconv bias of the pose head
+    net.params["res5a_up_pose"][1].data[...] = w2["res5a_up_pose"][1]
+    b = netutil.product_forward(net, x)
+    ref = netutil.oracle_forward(path, w2, x)
+    assert netutil.max_err(b["prob"], ref["prob"]) < 1e-4 and netutil.max_err(a["prob"], b["prob"]) > 1e-2
+    # weights through a .caffemodel file give the same result as through the param views
+    model = os.path.join(str(tmp_path), "w.caffemodel")
+    net.save(model)
+    caffe = dcutil.caffe_module()
+    net2 = caffe.Net(path, model, caffe.TEST)
+    c = netutil.product_forward(net2, x)
+    for k in b:
+        assert np.array_equal(b[k], c[k]), k
+
+
+@pytest.mark.parametrize("stages,h,w,n", [((3, 4, 23, 3), 128, 160, 1), ((3, 8, 36, 3), 256, 256, 1)])
+def test_full_depth_nets_match_oracle(tmp_path, stages, h, w, n):
+    # config[0]/[1] geometry of BASELINE.json at the oracle's comfortable size: the shipped ResNet-152
+    # deploy net at 1x3x256x256, and the ResNet-101 variant
+    path, weights = netutil.build(tmp_path, stages, h, w)
+    x = dcutil.synth.images(n, h, w)
+    ref = netutil.oracle_forward(path, weights, x)
+    net = netutil.product_net(path, weights)
+    got = netutil.product_forward(net, x)
+    assert net.fused_last_forward, net.fusion_diagnostic
+    errs = _report("ResNet stages %s %dx%d" % (stages, h, w), got, ref)
+    assert max(errs.values()) < TOL
+    assert 0.01 < got["prob"].min() and got["prob"].max() < 0.99
