@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- DeeperCut forward throughput on B200 (images/s), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            the B200-native path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU algorithm (oracle) on host cores
+
+A "step" = one Net::Forward over one batch of synthetic images.  Default workload: the shipped
+DeeperCut ResNet-152 deploy net, batch 16 of 3x720x1280 per GPU (BASELINE.json configs[2]; the
+scaling target of the north_star is quoted on 720p batches).  Weak scaling: every rank runs its own
+batch, no data-path collective in the device-timed region.
+
+  value   images/s over all ranks, inputs resident in HBM, CUDA events on the forward stream, max over ranks
+  e2e     same metric through the Caffe API with HOST buffers: per step the input blob is re-uploaded from
+          pinned host memory (H2D) and `prob` + `loc_pred` -- the two blobs the reference's caller reads,
+          python/pose/estimate_pose.py:231 -- are read back (D2H); for N > 1 rank 0 owns the global batch
+          and NCCL scatters inputs / gathers outputs over NVLink
+  roofline  conv_igemm (tcgen05) kernels: algorithmic 2*MAC FLOPs / summed device time of those launches
+  cpu_baseline  the oracle (numpy im2col + OpenBLAS sgemm restatement of the reference CPU path), rank 0, N = 1
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "deepcut-cnn_b200", "python"))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--height", type=int, default=720)
+    ap.add_argument("--width", type=int, default=1280)
+    ap.add_argument("--model", default="152", choices=["152", "101"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-report", default=None, help="write the per-step roofline table to this path")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json, sustained bf16 / copy bandwidth)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        # under load = the upper half of the samples (the sampler also sees idle gaps)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_net_files(args):
+    gen = importlib.import_module("deepcut-cnn_b200.gen_prototxt")
+    d = os.path.join(ROOT, "models", "_gen")
+    os.makedirs(d, exist_ok=True)
+    stages = gen.STAGES_152 if args.model == "152" else gen.STAGES_101
+    path = os.path.join(d, "bench_resnet%s_%dx%d_r%s.prototxt" % (args.model, args.height, args.width, os.environ.get("RANK", "0")))
+    gen.write(path, stages=stages, height=args.height, width=args.width)
+    return path
+
+
+def workload_name(args):
+    return "DeeperCut ResNet-%s deploy net (models/deepercut), fwd, batch %d/GPU, 3x%dx%d" % (args.model, args.batch, args.height, args.width)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path: it cannot be built here (no protobuf/glog/
+    boost/BLAS dev files), so this is the oracle port (numpy im2col + OpenBLAS sgemm), on all
+    host cores.  One step = one image of the workload (a bounded sample); rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import caffe_ref
+    synth = importlib.import_module("deepcut-cnn_b200.synth")
+    ptx = importlib.import_module("deepcut-cnn_b200.prototxt")
+    path = build_net_files(args)
+    net = caffe_ref.load_net(path)
+    net.params = synth.weights(net.typed_param_shapes())       # values do not affect CPU time
+    x = synth.images(1, args.height, args.width)
+    net.reshape_input("data", x.shape)
+    for _ in range(args.warmup):
+        net.forward({"data": x})
+    t0 = time.time()
+    for _ in range(args.steps):
+        net.forward({"data": x})
+    dt = (time.time() - t0) / args.steps
+    cores = os.cpu_count()
+    v = 1.0 / dt
+    line = {"impl": "reference", "metric": "part-scoremap images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": "1 image per step on host cores"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "1 image 3x%dx%d per step, numpy im2col + OpenBLAS sgemm oracle" % (args.height, args.width)},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import caffe
+    libdc = importlib.import_module("deepcut-cnn_b200.libdc")
+    synth = importlib.import_module("deepcut-cnn_b200.synth")
+    ptx = importlib.import_module("deepcut-cnn_b200.prototxt")
+    L = libdc.lib()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+    caffe.set_mode_gpu()
+    caffe.set_device(local_rank)
+    stream = C.c_void_p(caffe._caffe.lib.caffe_stream())
+
+    path = build_net_files(args)
+    net = caffe.Net(path, caffe.TEST)
+    net.set_params(synth.calibrated_weights(ptx.parse_file(path)))
+    B, H, W = args.batch, args.height, args.width
+    net.blobs["data"].reshape(B, 3, H, W)
+    x = synth.images(B, H, W, seed=20160505 + rank)
+    net.blobs["data"].data[...] = x
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        caffe.sync()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = C.c_void_p(), C.c_void_p()
+        libdc.check(L.dc_event_create(C.byref(e0)))
+        libdc.check(L.dc_event_create(C.byref(e1)))
+        barrier()
+        t0 = time.time()
+        libdc.check(L.dc_event_record(e0, stream))
+        for _ in range(steps):
+            fn()
+        libdc.check(L.dc_event_record(e1, stream))
+        caffe.sync()
+        wall = time.time() - t0
+        ms = C.c_float()
+        libdc.check(L.dc_event_elapsed_ms(e0, e1, C.byref(ms)))
+        barrier()
+        L.dc_event_destroy(e0)
+        L.dc_event_destroy(e1)
+        t = torch.tensor([ms.value, wall * 1e3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    # ---- device-resident throughput
+    net.forward()                       # builds the plan, packs weights, uploads the input
+    assert net.fused_last_forward, "fused plan not active: " + net.fusion_diagnostic
+    for _ in range(max(args.warmup, 3) - 1):
+        net.forward()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.dc_launch_count()
+    dev_ms, wall_ms = timed(net.forward, args.steps)
+    launches = L.dc_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (dev_ms / 1e3)
+
+    # ---- end to end through the Caffe API with host buffers
+    prob, loc = net.blobs["prob"], net.blobs["loc_pred"]
+    h2d = B * 3 * H * W * 4
+    d2h = (prob.count + loc.count) * 4
+    if dist is None:
+        def e2e_step():
+            net.blobs["data"].data          # host write access: the pinned host copy is authoritative again -> H2D next forward
+            net.forward()
+            prob.data                       # D2H + sync (what estimate_pose.py reads)
+            loc.data
+    else:
+        dmod = importlib.import_module("deepcut-cnn_b200.dist")
+        ex = dmod.BatchExchange(dist, rank, world, (B, 3, H, W), {"prob": prob.shape, "loc_pred": loc.shape}, x if rank == 0 else None)
+        h2d, d2h = ex.h2d_bytes, ex.d2h_bytes
+
+        def e2e_step():
+            ex.scatter_into(net.blobs["data"], L, stream)
+            net.forward()
+            ex.gather_from({"prob": prob, "loc_pred": loc}, L, stream)
+    for _ in range(2):
+        e2e_step()
+    _, e2e_wall_ms = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (e2e_wall_ms / 1e3)     # host wall clock: includes every copy and sync
+
+    # ---- per-step roofline pass (separate from the timed region: events around every step)
+    roofline = None
+    report = None
+    if rank == 0:
+        pk = peaks()
+        net.set_step_timing(True)
+        net.forward()
+        caffe.sync()
+        info = net.step_info()
+        net.set_step_timing(False)
+        conv = [s for s in info if s[0] in ("ConvBN", "HeadGemm")]
+        cflops = sum(s[3] for s in conv)
+        cms = sum(s[2] for s in conv)
+        total_ms = sum(s[2] for s in info)
+        ach = cflops / (cms / 1e3) / 1e12
+        roofline = {"kernel": "conv_igemm_kernel (tcgen05 kind::f16, split-fp16 x3)", "bound": "tensor", "achieved": ach, "peak": pk["tflops"],
+                    "unit": "TFLOP/s", "frac": ach / pk["tflops"], "issued_frac": 3 * ach / pk["tflops"], "mma_passes": 3,
+                    "share_of_step": cms / total_ms, "launches": len(conv), "peak_source": pk["source"], "traffic": None}
+        report = {"total_ms": total_ms, "steps": [{"type": s[0], "name": s[1], "ms": s[2], "gflop": s[3] / 1e9, "mbytes": s[4] / 1e6,
+                                                    "tflops": (s[3] / (s[2] / 1e3) / 1e12) if s[2] > 0 else 0.0,
+                                                    "gbs": (s[4] / (s[2] / 1e3) / 1e9) if s[2] > 0 else 0.0} for s in info]}
+        if args.step_report:
+            os.makedirs(os.path.dirname(os.path.abspath(args.step_report)), exist_ok=True)
+            json.dump(report, open(args.step_report, "w"), indent=1)
+
+    # ---- CPU baseline (oracle port), rank 0 at N = 1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import caffe_ref
+        onet = caffe_ref.load_net(path)
+        onet.params = synth.weights(onet.typed_param_shapes())
+        x1 = x[:1]
+        onet.reshape_input("data", x1.shape)
+        onet.forward({"data": x1})
+        t0 = time.time()
+        reps = 2
+        for _ in range(reps):
+            onet.forward({"data": x1})
+        dt = (time.time() - t0) / reps
+        cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": "1 image 3x%dx%d, %d timed forwards after 1 warm-up, numpy im2col + OpenBLAS sgemm oracle" % (H, W, reps)}
+
+    if rank == 0:
+        line = {"metric": "part-scoremap images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16x2 split operands, f32 accumulate (3 tcgen05 passes)", "data": "synthetic",
+                "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "l2_policy": "inputs larger than L2 (per-step activations >> 126 MB)", "outputs": "prob, loc_pred, next_pred"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred"},
+                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "wall_ms_per_step": wall_ms / args.steps, "arena_mib": net.arena_bytes >> 20, "weights_mib": net.weight_bytes >> 20}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,12 @@ class FusedPlan {
   size_t weight_bytes() const { return weight_bytes_; }
   int num_steps() const { return static_cast<int>(steps_.size()); }
   std::string Describe() const;
+  // Per-step device timing: when enabled Run() brackets every step with CUDA events on the forward
+  // stream (the reference's `caffe time` idiom, tools/caffe.cpp:302-388, per fused step instead of
+  // per layer).  StepInfo gives the last run's duration and the step's algorithmic work.
+  struct StepInfo { std::string name, type; double ms, flops, bytes; };
+  void set_step_timing(bool on) { step_timing_ = on; }
+  std::vector<StepInfo> LastStepInfo();
 
   struct Tensor;
   struct Step;
@@ -51,6 +57,8 @@ class FusedPlan {
   std::vector<void*> weight_allocs_;
   std::vector<int> split_layers_;     // Split layer ids to alias after a materialised run
   bool materialize_ = false;
+  bool step_timing_ = false;
+  std::vector<void*> events_;
   std::vector<std::pair<SyncedMemory*, unsigned long long> > weight_epochs_;
 };
 

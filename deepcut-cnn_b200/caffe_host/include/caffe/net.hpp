@@ -78,6 +78,8 @@ class Net {
   // Device kernels launched by the last ForwardPrefilled.
   long long last_forward_launches() const { return last_launches_; }
   void InvalidatePlan();
+  void set_step_timing(bool on) { step_timing_ = on; }
+  FusedPlan* plan() const { return plan_; }
 
  protected:
   void AppendTop(const NetParameter& param, const int layer_id, const int top_id, set<string>* available_blobs, map<string, int>* blob_name_to_idx);
@@ -108,6 +110,7 @@ class Net {
 
   bool fusion_ = true;
   bool materialize_ = false;
+  bool step_timing_ = false;
   bool fused_last_forward_ = false;
   string fusion_diag_;
   long long last_launches_ = 0;

@@ -117,6 +117,25 @@ int caffe_net_fused_last_forward(void* net) { return N(net)->fused_last_forward(
 const char* caffe_net_fusion_diagnostic(void* net) { return N(net)->fusion_diagnostic().c_str(); }
 long long caffe_net_last_forward_launches(void* net) { return N(net)->last_forward_launches(); }
 
+int caffe_net_set_step_timing(void* net, int on) { return Guard([&] { N(net)->set_step_timing(on != 0); }); }
+int caffe_net_num_steps(void* net) { return N(net)->plan() ? N(net)->plan()->num_steps() : 0; }
+int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, double* flops, double* bytes, int max_steps) {
+  return Guard([&] {
+    CHECK(N(net)->plan()) << "no fused plan (run a GPU forward first)";
+    std::vector<FusedPlan::StepInfo> info = N(net)->plan()->LastStepInfo();
+    CHECK_LE((int)info.size(), max_steps);
+    std::string all;
+    for (size_t i = 0; i < info.size(); ++i) {
+      all += info[i].type + " " + info[i].name + "\n";
+      ms[i] = info[i].ms; flops[i] = info[i].flops; bytes[i] = info[i].bytes;
+    }
+    CHECK_LT((int)all.size(), names_cap);
+    memcpy(names, all.c_str(), all.size() + 1);
+  });
+}
+long long caffe_net_arena_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->arena_bytes() : 0; }
+long long caffe_net_weight_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->weight_bytes() : 0; }
+
 int caffe_insert_splits_text(const char* prototxt_text, char* out, int out_cap) {
   return Guard([&] {
     NetParameter p, q;

@@ -54,6 +54,7 @@ FusedPlan::~FusedPlan() {
   for (Tensor* t : tensors_) delete t;
   for (Step* s : steps_) delete s;
   for (void* p : weight_allocs_) dc_free(p);
+  for (void* e : events_) dc_event_destroy(e);
   if (arena_) dc_free(arena_);
 }
 
@@ -604,7 +605,15 @@ void FusedPlan::Run() {
   Net<float>& net = *net_;
   void* stream = Caffe::stream();
   auto blob_in = [&](Tensor* t) { return net.blobs()[t->blob]->gpu_data(); };
+  if (step_timing_ && events_.size() != steps_.size() + 1) {
+    for (void* e : events_) dc_event_destroy(e);
+    events_.assign(steps_.size() + 1, nullptr);
+    for (void*& e : events_) DC_CHECK(dc_event_create(&e));
+  }
+  size_t step_index = 0;
   for (Step* st : steps_) {
+    if (step_timing_) DC_CHECK(dc_event_record(events_[step_index], stream));
+    ++step_index;
     switch (st->type) {
       case Step::kConv1: {
         DC_CHECK(dc_conv1_forward(blob_in(st->in), st->in->n, st->in->h, st->in->w, static_cast<const float*>(st->w_dev), st->scale_dev,
@@ -646,7 +655,61 @@ void FusedPlan::Run() {
       }
     }
   }
+  if (step_timing_) DC_CHECK(dc_event_record(events_[step_index], stream));
   for (int l : split_layers_) net.layers()[l]->Forward(net.bottom_vecs()[l], net.top_vecs()[l]);
+}
+
+std::vector<FusedPlan::StepInfo> FusedPlan::LastStepInfo() {
+  static const char* kNames[] = {"Conv1", "ConvBN", "Subsample", "MaxPool", "HeadGemm", "HeadFinish", "ToBlob"};
+  std::vector<StepInfo> out;
+  for (size_t i = 0; i < steps_.size(); ++i) {
+    const Step* st = steps_[i];
+    StepInfo si;
+    si.name = st->name;
+    si.type = kNames[st->type];
+    si.ms = 0;
+    if (events_.size() == steps_.size() + 1) {
+      float ms = 0.f;
+      DC_CHECK(dc_event_elapsed_ms(events_[i], events_[i + 1], &ms));
+      si.ms = ms;
+    }
+    si.flops = 0;
+    si.bytes = 0;
+    auto tbytes = [](const Tensor* t) -> double {
+      if (!t) return 0;
+      if (t->kind == Tensor::kF32Rows) return 4.0 * t->n * t->h * t->w * t->ld;
+      return 4.0 * t->elems();         // split fp16 hi+lo and fp32 blobs are both 4 B / element
+    };
+    switch (st->type) {
+      case Step::kConv1: {
+        si.flops = 2.0 * st->out->elems() * 147;
+        si.bytes = tbytes(st->in) + tbytes(st->out) + 147 * 64 * 4;
+        break;
+      }
+      case Step::kConvBN: {
+        const double K = static_cast<double>(st->kh) * st->kw * st->in->c;
+        si.flops = 2.0 * st->out->elems() * K;
+        si.bytes = tbytes(st->in) + tbytes(st->out) + tbytes(st->in2) + 4.0 * K * st->cout;
+        break;
+      }
+      case Step::kHeadGemm: {
+        const double pix = static_cast<double>(st->in->n) * st->in->h * st->in->w;
+        si.flops = 2.0 * pix * st->cout * st->in->c;
+        si.bytes = tbytes(st->in) + 4.0 * pix * st->cout + 4.0 * st->in->c * st->cout;
+        break;
+      }
+      case Step::kHeadFinish: {
+        Blob<float>* ob = net_->blobs()[st->out_blob].get();
+        si.bytes = 4.0 * ob->count() * 2 + 4.0 * st->in->n * st->in->h * st->in->w * st->cout * 9;
+        break;
+      }
+      case Step::kSubsample: si.bytes = 2 * tbytes(st->out); break;
+      case Step::kMaxPool: si.bytes = tbytes(st->in) + tbytes(st->out); break;
+      case Step::kToBlob: si.bytes = 2 * tbytes(st->in); break;
+    }
+    out.push_back(si);
+  }
+  return out;
 }
 
 std::string FusedPlan::Describe() const {

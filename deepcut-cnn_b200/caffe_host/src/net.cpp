@@ -204,6 +204,7 @@ const vector<Blob<Dtype>*>& Net<Dtype>::ForwardPrefilled(Dtype* loss) {
       if (plan_ == nullptr) LOG(WARNING) << "fused plan unavailable (" << fusion_diag_ << "); running layer by layer";
     }
     if (plan_ != nullptr) {
+      plan_->set_step_timing(step_timing_);
       plan_->Run();
       fused_last_forward_ = true;
       last_launches_ = dc_launch_count() - launches_before;

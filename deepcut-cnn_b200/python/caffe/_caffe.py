@@ -45,6 +45,10 @@ def _load():
         "caffe_net_fused_last_forward": (ci, [vp]), "caffe_net_fusion_diagnostic": (cs, [vp]),
         "caffe_net_last_forward_launches": (C.c_longlong, [vp]),
         "caffe_insert_splits_text": (ci, [cs, C.c_char_p, ci]),
+        "caffe_net_set_step_timing": (ci, [vp, ci]), "caffe_net_num_steps": (ci, [vp]),
+        "caffe_net_step_info": (ci, [vp, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), ci]),
+        "caffe_net_arena_bytes": (C.c_longlong, [vp]), "caffe_net_weight_bytes": (C.c_longlong, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

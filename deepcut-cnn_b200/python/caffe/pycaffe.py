@@ -221,6 +221,28 @@ class Net(object):
     def last_forward_launches(self):
         return lib.caffe_net_last_forward_launches(self._h)
 
+    def set_step_timing(self, on):
+        check(lib.caffe_net_set_step_timing(self._h, int(bool(on))))
+
+    def step_info(self):
+        """[(type, name, ms, flops, bytes)] for the fused steps of the last forward."""
+        n = lib.caffe_net_num_steps(self._h)
+        if n == 0:
+            return []
+        names = C.create_string_buffer(256 * n)
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        check(lib.caffe_net_step_info(self._h, names, len(names), ms, fl, by, n))
+        rows = names.value.decode().strip().split("\n")
+        return [(r.split(" ", 1)[0], r.split(" ", 1)[1], ms[i], fl[i], by[i]) for i, r in enumerate(rows)]
+
+    @property
+    def arena_bytes(self):
+        return lib.caffe_net_arena_bytes(self._h)
+
+    @property
+    def weight_bytes(self):
+        return lib.caffe_net_weight_bytes(self._h)
+
     def set_params(self, weights):
         """weights: {layer name: [arrays]} written through the param views (harness helper)."""
         params = self.params

@@ -62,6 +62,13 @@ int caffe_net_materialize_intermediates(void* net, int on);
 int caffe_net_fused_last_forward(void* net);
 const char* caffe_net_fusion_diagnostic(void* net);
 long long caffe_net_last_forward_launches(void* net);
+/* Per-step device timing of the fused plan (the `caffe time` idiom, tools/caffe.cpp:302-388).
+ * names receives "Type name\n" per step; ms/flops/bytes the last run's duration and algorithmic work. */
+int caffe_net_set_step_timing(void* net, int on);
+int caffe_net_num_steps(void* net);
+int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, double* flops, double* bytes, int max_steps);
+long long caffe_net_arena_bytes(void* net);
+long long caffe_net_weight_bytes(void* net);
 int caffe_insert_splits_text(const char* prototxt_text, char* out, int out_cap);   /* InsertSplits, insert_splits.cpp:12 */
 
 #ifdef __cplusplus
