@@ -307,12 +307,14 @@ struct Matcher {
     const int h5 = x5->h, w5 = x5->w, h3 = x3->h, w3 = x3->w;
     if (!(2 * h5 + 1 > h3 && 2 * w5 + 1 > w3 && h3 <= 2 * h5 + 1)) return Fail("head geometry: crop larger than the deconvolution output");
     // merged deconv GEMM -> col rows, merged 1x1 GEMM -> skip rows
-    FusedPlan::Tensor* col = NewInternal(FusedPlan::Tensor::kF32Rows, x5->n, dc_packed_rows(ctot * 9), h5, w5);
-    col->ld = dc_packed_rows(ctot * 9);
+    // channel-major fp32 results: rows = packed weight rows, ld = pixels rounded up to 32
+    auto round32 = [](long long v) { return static_cast<int>((v + 31) / 32 * 32); };
+    FusedPlan::Tensor* col = NewInternal(FusedPlan::Tensor::kF32Rows, 1, 1, dc_packed_rows(ctot * 9), 1);
+    col->ld = round32(static_cast<long long>(x5->n) * h5 * w5);
     FusedPlan::Step* g1 = AddStep(FusedPlan::Step::kHeadGemm, "heads/deconv_gemm");
     g1->in = x5; g1->out = col; g1->deconv_rows = true; g1->cout = ctot * 9;
-    FusedPlan::Tensor* srows = NewInternal(FusedPlan::Tensor::kF32Rows, x3->n, dc_packed_rows(ctot), h3, w3);
-    srows->ld = dc_packed_rows(ctot);
+    FusedPlan::Tensor* srows = NewInternal(FusedPlan::Tensor::kF32Rows, 1, 1, dc_packed_rows(ctot), 1);
+    srows->ld = round32(static_cast<long long>(x3->n) * h3 * w3);
     FusedPlan::Step* g2 = AddStep(FusedPlan::Step::kHeadGemm, "heads/skip_gemm");
     g2->in = x3; g2->out = srows; g2->deconv_rows = false; g2->cout = ctot;
     int off = 0;
@@ -629,7 +631,7 @@ void FusedPlan::Run() {
         a.w_packed = st->w_dev; a.scale = st->scale_dev; a.shift = st->shift_dev;
         a.residual = st->in2 && st->type == Step::kConvBN ? st->in2->ptr : nullptr;
         a.relu = st->relu;
-        a.out_f32_rows = st->type == Step::kHeadGemm;
+        a.out_f32_rows = st->type == Step::kHeadGemm ? 2 : 0;
         a.ldc = st->out->ld;
         a.out = st->out->ptr;
         DC_CHECK(dc_conv_forward(&a, stream));

@@ -20,8 +20,10 @@
 //   warp 0   TMA producer: 4 bulk-tensor loads / stage (A_hi, A_lo: 5-D NHWC boxes with
 //            negative/OOB coordinates zero-filled = padding & dilation; B_hi, B_lo)
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees stages
-//   warps 2-5 epilogue: tcgen05.ld accumulator -> *scale[c] + shift[c] (+ residual) (ReLU)
-//            -> split fp16 NHWC stores (or fp32 rows for the head GEMMs)
+//   warps 2-9 epilogue (two per TMEM lane quarter): tcgen05.ld main + cross accumulators ->
+//            *scale[c] + shift[c] (+ residual) (ReLU) -> split fp16 NHWC stores; or fp32 rows for
+//            the head GEMMs, which run with A and B swapped (weights on the 128 accumulator
+//            lanes, pixels on the columns) so their output is channel-major like Caffe's col buffer
 //   TMEM holds two (main, cross) accumulator pairs so the epilogue of tile i overlaps the MMAs
 //   of tile i+1: 4 * BN columns, hence BN <= 128.
 #pragma once
@@ -32,9 +34,9 @@ namespace dc {
 constexpr int kBM = 128;        // output pixels per tile (TMEM lanes)
 constexpr int kBK = 64;         // fp16 channels per K-chunk = one 128-byte swizzle row
 constexpr int kMaxTaps = 9;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;    // TMA warp, MMA warp, 8 epilogue warps
 
-enum OutMode : int { kOutSplitNHWC = 0, kOutF32Rows = 1 };
+enum OutMode : int { kOutSplitNHWC = 0, kOutF32Rows = 1, kOutF32RowsT = 2 };
 
 struct ConvParams {
   int H, W;                 // input spatial dims as seen by the A tensor map
@@ -56,6 +58,7 @@ struct ConvParams {
   int ldc;                  // row stride in floats (fp32-rows mode)
   int relu;
   int out_mode;
+  int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
 };
 
 template <int BN>
@@ -100,7 +103,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_mbar_init();
   }
@@ -164,10 +167,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);   // 16 fp16 = 32 B along K
-            umma_f16(d, a_hi + adv, b_hi + adv, idesc, accum);
-            umma_f16(dx, a_hi + adv, b_lo + adv, idesc, accum);
-            accum = 1;
-            umma_f16(dx, a_lo + adv, b_hi + adv, idesc, 1);
+            // hi*hi, hi*lo and lo*hi are symmetric in (A, B): swapping the operands only transposes D
+            if (p.swap_ab) {
+              umma_f16(d, b_hi + adv, a_hi + adv, idesc, accum);
+              umma_f16(dx, b_hi + adv, a_lo + adv, idesc, accum);
+              accum = 1;
+              umma_f16(dx, b_lo + adv, a_hi + adv, idesc, 1);
+            } else {
+              umma_f16(d, a_hi + adv, b_hi + adv, idesc, accum);
+              umma_f16(dx, a_hi + adv, b_lo + adv, idesc, accum);
+              accum = 1;
+              umma_f16(dx, a_lo + adv, b_hi + adv, idesc, 1);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -178,9 +189,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter; they split the tile's 32-column chunks between them.
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;          // pixel row of the tile
+    const int half = (warp - 2) >> 2;       // which of the two warps of this quarter
+    const int row = q * 32 + lane;          // accumulator row (TMEM lane) this thread owns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -190,41 +203,70 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
       const int img = mt / p.tiles_y;
-      const int oy = ty * p.TH + row / p.TW;
-      const int ox = tx * p.TW + row % p.TW;
-      const bool valid = (oy < p.Ho) && (ox < p.Wo);
-      const long long pix = (static_cast<long long>(img) * p.Ho + oy) * p.Wo + ox;
       const int n0 = nt * BN;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 2 * BN);
+      if (p.out_mode == kOutF32RowsT) {
+        // swapped operands: row = weight row (output channel), columns = the tile's 128 pixels
+        // (flat 1x1 geometry: pixel = tx * 128 + column).  out[(n0 + row) * ldc + pixel], fp32.
+        const float sc = __ldg(p.scale + n0 + row), sh = __ldg(p.shift + n0 + row);
+        float* orow = reinterpret_cast<float*>(p.out) + static_cast<long long>(n0 + row) * p.ldc;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (p.out_mode == kOutSplitNHWC && n0 + c0 >= p.Cout) break;
-        uint32_t r[32], rx[32];
-        tmem_ld_32x32(taddr + c0, r);
-        tmem_ld_32x32(taddr + BN + c0, rx);
-        tmem_ld_wait();
-        float v[32];
+        for (int c0 = half * 32; c0 < kBM; c0 += 64) {
+          uint32_t r[32], rx[32];
+          tmem_ld_32x32(taddr + c0, r);
+          tmem_ld_32x32(taddr + BN + c0, rx);
+          tmem_ld_wait();
+          const int pix0 = tx * p.TW + c0;
+          if (pix0 + 32 <= p.Wo) {
+            float4* o = reinterpret_cast<float4*>(orow + pix0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), __ldg(p.scale + n0 + c0 + j),
-                      __ldg(p.shift + n0 + c0 + j));
-        if (p.out_mode == kOutSplitNHWC) {
-          const long long off = pix * p.Cout + n0 + c0;
-          if (valid) {
+            for (int g = 0; g < 8; ++g) {
+              float4 f;
+              f.x = fmaf(__uint_as_float(r[4 * g + 0]) + __uint_as_float(rx[4 * g + 0]), sc, sh);
+              f.y = fmaf(__uint_as_float(r[4 * g + 1]) + __uint_as_float(rx[4 * g + 1]), sc, sh);
+              f.z = fmaf(__uint_as_float(r[4 * g + 2]) + __uint_as_float(rx[4 * g + 2]), sc, sh);
+              f.w = fmaf(__uint_as_float(r[4 * g + 3]) + __uint_as_float(rx[4 * g + 3]), sc, sh);
+              o[g] = f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (pix0 + j < p.Wo) orow[pix0 + j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), sc, sh);
+          }
+        }
+      } else {
+        const int oy = ty * p.TH + row / p.TW;
+        const int ox = tx * p.TW + row % p.TW;
+        const bool valid = (oy < p.Ho) && (ox < p.Wo);
+        const long long pix = (static_cast<long long>(img) * p.Ho + oy) * p.Wo + ox;
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          if (p.out_mode == kOutSplitNHWC && n0 + c0 >= p.Cout) break;
+          uint32_t r[32], rx[32];
+          tmem_ld_32x32(taddr + c0, r);
+          tmem_ld_32x32(taddr + BN + c0, rx);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), __ldg(p.scale + n0 + c0 + j), __ldg(p.shift + n0 + c0 + j));
+          if (!valid) continue;
+          if (p.out_mode == kOutSplitNHWC) {
+            const long long off = pix * p.Cout + n0 + c0;
             if (p.res != nullptr) {
               const uint4* rh = reinterpret_cast<const uint4*>(p.res + off);
               const uint4* rl = reinterpret_cast<const uint4*>(p.res + p.res_plane + off);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
+                const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
                 const __half2* hh = reinterpret_cast<const __half2*>(&h4);
                 const __half2* ll = reinterpret_cast<const __half2*>(&l4);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
+                  const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
                   v[g * 8 + e * 2 + 0] += fh.x + fl.x;
                   v[g * 8 + e * 2 + 1] += fh.y + fl.y;
                 }
@@ -241,18 +283,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int e = 0; e < 4; ++e) {
                 float a = v[g * 8 + e * 2], b = v[g * 8 + e * 2 + 1];
                 if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                __half ah, al, bh, bl;
-                split_f16(a, ah, al);
-                split_f16(b, bh, bl);
-                hh[e] = __halves2half2(ah, bh);
-                ll[e] = __halves2half2(al, bl);
+                const __half2 h2 = __floats2half2_rn(a, b);          // one cvt.rn.f16x2.f32
+                const float2 hf = __half22float2(h2);
+                hh[e] = h2;
+                ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
               }
               reinterpret_cast<uint4*>(oh)[g] = h4;
               reinterpret_cast<uint4*>(ol)[g] = l4;
             }
-          }
-        } else {
-          if (valid) {
+          } else {   // kOutF32Rows
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldc + n0 + c0);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {

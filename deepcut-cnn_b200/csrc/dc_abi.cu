@@ -350,7 +350,13 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   if (ho <= 0 || wo <= 0) return fail(DC_ERR_INVALID, "dc_conv_forward: empty output");
   const int bn = tile_n_for(a->cout);
   const int rows = dc_packed_rows(a->cout);
-  if (a->out_f32_rows && a->ldc < rows) return fail(DC_ERR_INVALID, "dc_conv_forward: ldc=%d < packed rows %d", a->ldc, rows);
+  if (a->out_f32_rows == 1 && a->ldc < rows) return fail(DC_ERR_INVALID, "dc_conv_forward: ldc=%d < packed rows %d", a->ldc, rows);
+  if (a->out_f32_rows == 2) {
+    if (!(a->kh == 1 && a->kw == 1 && a->pad == 0) || bn != 128)
+      return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: channel-major output needs a 1x1 convolution with more than 64 outputs");
+    if (a->ldc < a->n * a->h * a->w || a->ldc % 4 != 0) return fail(DC_ERR_INVALID, "dc_conv_forward: ldc=%d must be >= n*h*w and a multiple of 4", a->ldc);
+    if (a->relu || a->residual) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: channel-major output has no ReLU/residual epilogue");
+  }
 
   dc::ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -388,7 +394,8 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.out_plane = out_elems;
   p.ldc = a->ldc;
   p.relu = a->relu;
-  p.out_mode = a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC;
+  p.out_mode = a->out_f32_rows == 2 ? dc::kOutF32RowsT : (a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC);
+  p.swap_ab = a->out_f32_rows == 2;
 
   CUtensorMap ta, tb;
   if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH)) return rc;
@@ -438,7 +445,7 @@ int dc_subsample_forward(const void* x, int n, int h, int w, int c, int stride, 
   return DC_OK;
 }
 
-int dc_head_finish(const float* col, int ldcol, int col_off, const float* skip, int ldskip, int skip_off,
+int dc_head_finish(const float* col, long long ldcol, int col_off, const float* skip, long long ldskip, int skip_off,
                    float* out, int n, int cout, int h, int w, int ho, int wo, int sigmoid, void* stream) {
   if (int rc = ensure_init()) return rc;
   if (!col || !skip || !out) return fail(DC_ERR_INVALID, "dc_head_finish: null argument");

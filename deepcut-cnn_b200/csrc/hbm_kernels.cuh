@@ -170,16 +170,18 @@ __global__ void __launch_bounds__(256) subsample_split_kernel(const __half* __re
 }
 
 // ---------------------------------------------------------------------------------------
-// Head finish.  Inputs are the two fp32 GEMM results of the merged heads:
-//   col  [N*h*w][ldcol]  col(pixel(i,j), co*9 + p*3 + q) = sum_ci res5c[ci,i,j] * Wd[ci,co,p,q]
-//   skip [N*Ho*Wo][ldskip] = 1x1 heads on res3b7 (+ both biases, folded into the GEMM shift)
+// Head finish.  Inputs are the two fp32 GEMM results of the merged heads, channel-major (the
+// layout of Caffe's own col buffer, base_conv_layer.cpp:358-365):
+//   col  [rows = co*9 + p*3 + q][ldcol >= N*h*w]   col(r, pixel(n,i,j)) = sum_ci res5c[n,ci,i,j] * Wd[ci,co,p,q]
+//   skip [rows = co][ldskip >= N*Ho*Wo]            1x1 heads on res3b7 (+ both biases, folded into the GEMM shift)
 // Output (fp32 NCHW, the layout Caffe exposes):  out[n,co,y,x] =
-//   skip + sum_{p,q : (y-p),(x-q) even, in range} col(((y-p)/2,(x-q)/2), co,p,q)  [-> sigmoid]
+//   skip + sum_{p,q : (y-p),(x-q) even, in range} col((co,p,q), (n,(y-p)/2,(x-q)/2))  [-> sigmoid]
 // i.e. DeconvolutionLayer col2im (im2col.cu:246-305) + Crop to Ho x Wo at offset 0
 // (crop_layer.cu:9-38) + Eltwise SUM (eltwise_layer.cu:47-53) + Sigmoid (sigmoid_layer.cu:8-24).
+// One thread per output element, x fastest: every read and the write are unit- or 2-strided rows.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ col, int ldcol, int col_off,
-                                                          const float* __restrict__ skip, int ldskip, int skip_off,
+__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ col, long long ldcol, int col_row0,
+                                                          const float* __restrict__ skip, long long ldskip, int skip_row0,
                                                           float* __restrict__ out, int N, int Cout, int h, int w,
                                                           int Ho, int Wo, int do_sigmoid) {
   const long long total = static_cast<long long>(N) * Cout * Ho * Wo;
@@ -201,11 +203,11 @@ __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restric
         const int xx = x - q;
         if (xx < 0 || (xx & 1) || (xx >> 1) >= w) continue;
         const long long pix = (static_cast<long long>(n) * h + (yy >> 1)) * w + (xx >> 1);
-        up += __ldg(col + pix * ldcol + col_off + co * 9 + p * 3 + q);
+        up += __ldg(col + (col_row0 + co * 9 + p * 3 + q) * ldcol + pix);
       }
     }
     const long long opix = (static_cast<long long>(n) * Ho + y) * Wo + x;
-    float v = __ldg(skip + opix * ldskip + skip_off + co) + up;
+    float v = __ldg(skip + (skip_row0 + co) * ldskip + opix) + up;
     if (do_sigmoid) v = 1.f / (1.f + expf(-v));
     out[i] = v;
   }

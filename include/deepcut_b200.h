@@ -101,8 +101,10 @@ typedef struct dc_conv_args {
   const float* shift;        /* device [dc_packed_rows(cout)]: folded b[c] (or bias) */
   const void* residual;      /* split NHWC, output geometry, or NULL (Eltwise SUM shortcut) */
   int relu;
-  int out_f32_rows;          /* 0: split NHWC out [2][n][ho][wo][cout]; 1: fp32 rows out[pixel][ldc] */
-  int ldc;                   /* fp32-rows mode: row stride in floats, >= dc_packed_rows(cout) */
+  int out_f32_rows;          /* 0: split NHWC out [2][n][ho][wo][cout]; 1: fp32 rows out[pixel][ldc];
+                              * 2: fp32 channel-major out[channel][ldc] (1x1 only; the GEMM runs with A and B
+                              *    swapped so its rows are Caffe's col-buffer rows, base_conv_layer.cpp:358-365) */
+  int ldc;                   /* row stride in floats: mode 1 >= dc_packed_rows(cout); mode 2 >= n*h*w, multiple of 4 */
   void* out;
 } dc_conv_args;
 /* Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-24) =
@@ -126,9 +128,10 @@ int dc_pool_out_size(int size, int kernel, int stride);
 int dc_subsample_forward(const void* x, int n, int h, int w, int c, int stride, void* out, void* stream);
 /* Head finish: col2im of the 3x3/2 deconvolution (im2col.cu:246-305) + Crop to (ho,wo) at offset 0
  * (crop_layer.cu:9-38) + Eltwise SUM with the 1x1 skip head (eltwise_layer.cu:47-53) [+ Sigmoid,
- * sigmoid_layer.cu:8-24].  col: fp32 [n*h*w][ldcol], column col_off + co*9 + p*3 + q;
- * skip: fp32 [n*ho*wo][ldskip], column skip_off + co; out: fp32 NCHW [n][cout][ho][wo]. */
-int dc_head_finish(const float* col, int ldcol, int col_off, const float* skip, int ldskip, int skip_off,
+ * sigmoid_layer.cu:8-24].  Both inputs are channel-major fp32 (dc_conv_forward out_f32_rows = 2):
+ * col row col_row0 + co*9 + p*3 + q, ldcol >= n*h*w; skip row skip_row0 + co, ldskip >= n*ho*wo;
+ * out: fp32 NCHW [n][cout][ho][wo]. */
+int dc_head_finish(const float* col, long long ldcol, int col_row0, const float* skip, long long ldskip, int skip_row0,
                    float* out, int n, int cout, int h, int w, int ho, int wo, int sigmoid, void* stream);
 /* Blob materialisation: fp32 NCHW <-> split NHWC. */
 int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream);

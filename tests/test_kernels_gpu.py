@@ -170,48 +170,61 @@ def test_subsample_and_layout_roundtrip(_gpu):
     assert np.array_equal(sub.cpu().numpy(), sp.cpu().numpy()[:, :, ::2, ::2, :])
 
 
+def _gemm_channel_major(_gpu, x_nchw, packed, scale, shift, cout):
+    """dc_conv_forward with out_f32_rows = 2 (operands swapped): returns fp32 [rows][ld]."""
+    L = libdc.lib()
+    n, ci, h, w = x_nchw.shape
+    rows = packed.shape[1]
+    ld = (n * h * w + 31) // 32 * 32
+    xs = _gpu.dev(dcutil.np_split(x_nchw))
+    out = torch.full((rows, ld), float("nan"), dtype=torch.float32, device="cuda")
+    dwp, dsc, dsh = _gpu.dev(packed), _gpu.dev(scale), _gpu.dev(shift)
+    args = libdc.ConvArgs(x=xs.data_ptr(), n=n, h=h, w=w, cin=ci, cout=cout, kh=1, kw=1, pad=0, dilation=1,
+                          w_packed=dwp.data_ptr(), scale=dsc.data_ptr(), shift=dsh.data_ptr(), residual=None,
+                          relu=0, out_f32_rows=2, ldc=ld, out=out.data_ptr())
+    libdc.check(L.dc_conv_forward(C.byref(args), _gpu.stream_ptr()))
+    torch.cuda.synchronize()
+    return out, ld
+
+
 def test_deconv_head_pipeline(_gpu):
-    """Deconvolution 3x3/2 + Crop + Eltwise(+1x1 skip conv with bias) + Sigmoid, as three ABI calls,
-    vs the oracle's layer-by-layer result (deconv_layer.cpp, crop_layer.cpp, eltwise, sigmoid)."""
+    """Deconvolution 3x3/2 + Crop + Eltwise(+1x1 skip conv with bias) + Sigmoid, as three ABI calls
+    (two channel-major GEMMs + finish), vs the oracle's layer-by-layer result (deconv_layer.cpp,
+    crop_layer.cpp, eltwise_layer.cpp, sigmoid_layer.cpp)."""
     L = libdc.lib()
     rng = np.random.default_rng(13)
-    n, c5, c3, h, w = 2, 256, 128, 6, 7
-    heads = (("pose", 14, True), ("locref", 28, False))
-    x5 = np.maximum(rng.standard_normal((n, c5, h, w)), 0).astype(np.float32)
-    x3 = np.maximum(rng.standard_normal((n, c3, 2 * h, 2 * w)), 0).astype(np.float32)
-    wd = [(rng.standard_normal((c5, co, 3, 3)) * 0.05).astype(np.float32) for _, co, _ in heads]
-    bd = [rng.normal(0, 0.1, co).astype(np.float32) for _, co, _ in heads]
-    ws = [(rng.standard_normal((co, c3, 1, 1)) * 0.05).astype(np.float32) for _, co, _ in heads]
-    bs = [rng.normal(0, 0.1, co).astype(np.float32) for _, co, _ in heads]
-    # merged GEMMs
-    wd_all = np.concatenate(wd, axis=1)
-    ws_all = np.concatenate(ws, axis=0)
-    ctot = wd_all.shape[1]
-    packed, rs = dcutil.pack_deconv(wd_all)
-    rows = packed.shape[1]
-    x5s = _gpu.dev(dcutil.np_split(x5))
-    col = torch.zeros((n * h * w, rows), dtype=torch.float32, device="cuda")
-    dwp, dsc, dsh = _gpu.dev(packed), _gpu.dev(rs), _gpu.dev(np.zeros(rows, np.float32))
-    args = libdc.ConvArgs(x=x5s.data_ptr(), n=n, h=h, w=w, cin=c5, cout=ctot * 9, kh=1, kw=1, pad=0, dilation=1,
-                          w_packed=dwp.data_ptr(), scale=dsc.data_ptr(), shift=dsh.data_ptr(), residual=None,
-                          relu=0, out_f32_rows=1, ldc=rows, out=col.data_ptr())
-    libdc.check(L.dc_conv_forward(C.byref(args), _gpu.stream_ptr()))
-    skip_rows = _gpu.conv_bn(x3, ws_all, np.ones(ctot, np.float32), np.concatenate(bs) + np.concatenate(bd),
-                             relu=False, f32_rows=True)
-    dskip = _gpu.dev(skip_rows)
-    off = 0
-    for i, (name, co, sig) in enumerate(heads):
-        up = caffe_ref.deconvolution(x5, wd[i], bd[i], 2, 0, 1)
-        sk = caffe_ref.convolution(x3, ws[i], bs[i], 1, 0, 1)
-        ref = caffe_ref.eltwise_sum([sk, caffe_ref.crop(up, sk)])
-        if sig:
-            ref = caffe_ref.sigmoid(ref)
-        out = torch.zeros((n, co, 2 * h, 2 * w), dtype=torch.float32, device="cuda")
-        libdc.check(L.dc_head_finish(col.data_ptr(), rows, off * 9, dskip.data_ptr(), skip_rows.shape[1], off,
-                                     out.data_ptr(), n, co, h, w, 2 * h, 2 * w, int(sig), _gpu.stream_ptr()))
-        torch.cuda.synchronize()
-        assert np.abs(out.cpu().numpy() - ref).max() < 2e-5, name
-        off += co
+    for (n, h, w) in ((2, 6, 7), (1, 11, 13)):        # n*h*w not a multiple of 128: ragged pixel tiles
+        c5, c3 = 256, 128
+        heads = (("pose", 14, True), ("locref", 28, False), ("next", 100, False))
+        x5 = np.maximum(rng.standard_normal((n, c5, h, w)), 0).astype(np.float32)
+        x3 = np.maximum(rng.standard_normal((n, c3, 2 * h, 2 * w)), 0).astype(np.float32)
+        wd = [(rng.standard_normal((c5, co, 3, 3)) * 0.05).astype(np.float32) for _, co, _ in heads]
+        bd = [rng.normal(0, 0.1, co).astype(np.float32) for _, co, _ in heads]
+        ws = [(rng.standard_normal((co, c3, 1, 1)) * 0.05).astype(np.float32) for _, co, _ in heads]
+        bs = [rng.normal(0, 0.1, co).astype(np.float32) for _, co, _ in heads]
+        ctot = sum(co for _, co, _ in heads)
+        packed, rs = dcutil.pack_deconv(np.concatenate(wd, axis=1))
+        col, ldcol = _gemm_channel_major(_gpu, x5, packed, rs, np.zeros_like(rs), ctot * 9)
+        packed2, rs2 = dcutil.pack_conv(np.concatenate(ws, axis=0))
+        shift2 = np.zeros_like(rs2)
+        shift2[:ctot] = np.concatenate(bs) + np.concatenate(bd)
+        skip, ldskip = _gemm_channel_major(_gpu, x3, packed2, rs2, shift2, ctot)
+        # the channel-major GEMM result is Caffe's col buffer: W^T x per pixel
+        ref_col = np.einsum("nchw,cr->rnhw", x5.astype(np.float64), np.concatenate(wd, axis=1).reshape(c5, -1).astype(np.float64))
+        assert np.abs(col.cpu().numpy()[:ctot * 9, :n * h * w] - ref_col.reshape(ctot * 9, -1)).max() < 1e-4
+        off = 0
+        for i, (name, co, sig) in enumerate(heads):
+            up = caffe_ref.deconvolution(x5, wd[i], bd[i], 2, 0, 1)
+            sk = caffe_ref.convolution(x3, ws[i], bs[i], 1, 0, 1)
+            ref = caffe_ref.eltwise_sum([sk, caffe_ref.crop(up, sk)])
+            if sig:
+                ref = caffe_ref.sigmoid(ref)
+            out = torch.zeros((n, co, 2 * h, 2 * w), dtype=torch.float32, device="cuda")
+            libdc.check(L.dc_head_finish(col.data_ptr(), ldcol, off * 9, skip.data_ptr(), ldskip, off, out.data_ptr(), n, co, h, w,
+                                         2 * h, 2 * w, int(sig), _gpu.stream_ptr()))
+            torch.cuda.synchronize()
+            assert np.abs(out.cpu().numpy() - ref).max() < 2e-5, name
+            off += co
 
 
 def test_launch_counter_moves(_gpu):
