@@ -69,19 +69,21 @@ struct ConvCfg {
   static_assert(BN == 64 || BN == 128, "4 accumulators of BN columns must fit 512 TMEM columns");
   static constexpr int kStages = (BN >= 128 ? 3 : 4);
   static constexpr int kTmemCols = 4 * BN;                         // 2 x (main, cross)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 4096;         // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo}
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* staging_all = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging_all + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tfull_bar = bars + 2 * kStages;
@@ -97,6 +99,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.out_mode == kOutSplitNHWC) prefetch_tmap(&tmO);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -237,68 +240,124 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (pix0 + j < p.Wo) orow[pix0 + j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), sc, sh);
           }
         }
-      } else {
+      } else if (p.out_mode == kOutSplitNHWC) {
+        // Coalesced path: the warp's 32 pixels x 32 channels chunk is staged in shared memory in the
+        // TMA SWIZZLE_64B layout ([row][64 B], 16-byte piece index ^= (row >> 1) & 3, which is also
+        // bank-conflict free for both access patterns below).  The residual is fetched cooperatively
+        // (lane -> 16 B piece (lane & 3) of rows (lane >> 2) + 8 i: full 32 B sectors), the result
+        // leaves through two TMA bulk-tensor stores (hi and lo plane) that clip ragged tile edges.
+        uint8_t* stg = staging_all + (warp - 2) * 4096;
+        const int sub_w = p.TW < 32 ? p.TW : 32;           // the warp's 32 rows form a sub_w x (32/sub_w) box
+        const int r0 = q * 32;
+        const int box_x = tx * p.TW + r0 % p.TW, box_y = ty * p.TH + r0 / p.TW;
+        long long coop_off[4];
+        bool coop_ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = r0 + (lane >> 2) + 8 * i;
+          const int yy = ty * p.TH + rr / p.TW, xx = tx * p.TW + rr % p.TW;
+          coop_ok[i] = (yy < p.Ho) && (xx < p.Wo);
+          coop_off[i] = ((static_cast<long long>(img) * p.Ho + yy) * p.Wo + xx) * p.Cout;
+        }
+        const int piece = lane & 3;
+        const int own_sw = (lane >> 1) & 3;                // swizzle of this thread's own row (row index == lane)
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          if (n0 + c0 >= p.Cout) break;
+          uint32_t r[32], rx[32];
+          tmem_ld_32x32(taddr + c0, r);
+          tmem_ld_32x32(taddr + BN + c0, rx);
+          if (lane == 0) tma_store_wait_read();            // previous chunk's stores have drained the staging tile
+          __syncwarp();
+          if (p.res != nullptr) {
+            uint4 hv[4], lv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              hv[i] = make_uint4(0, 0, 0, 0);
+              lv[i] = make_uint4(0, 0, 0, 0);
+              if (coop_ok[i]) {
+                const __half* src = p.res + coop_off[i] + n0 + c0 + piece * 8;
+                hv[i] = __ldg(reinterpret_cast<const uint4*>(src));
+                lv[i] = __ldg(reinterpret_cast<const uint4*>(src + p.res_plane));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (lane >> 2) + 8 * i;
+              const int sw = (rr >> 1) & 3;
+              *reinterpret_cast<uint4*>(stg + rr * 64 + ((piece ^ sw) << 4)) = hv[i];
+              *reinterpret_cast<uint4*>(stg + 2048 + rr * 64 + ((piece ^ sw) << 4)) = lv[i];
+            }
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), __ldg(p.scale + n0 + c0 + j), __ldg(p.shift + n0 + c0 + j));
+          uint8_t* my_hi = stg + lane * 64;
+          uint8_t* my_lo = my_hi + 2048;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int slot = (g ^ own_sw) << 4;
+            if (p.res != nullptr) {
+              const uint4 h4 = *reinterpret_cast<const uint4*>(my_hi + slot);
+              const uint4 l4 = *reinterpret_cast<const uint4*>(my_lo + slot);
+              const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+              const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
+                v[g * 8 + e * 2 + 0] += fh.x + fl.x;
+                v[g * 8 + e * 2 + 1] += fh.y + fl.y;
+              }
+            }
+            uint4 h4, l4;
+            __half2* hh = reinterpret_cast<__half2*>(&h4);
+            __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = v[g * 8 + e * 2], b = v[g * 8 + e * 2 + 1];
+              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              const __half2 h2 = __floats2half2_rn(a, b);
+              const float2 hf = __half22float2(h2);
+              hh[e] = h2;
+              ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+            }
+            *reinterpret_cast<uint4*>(my_hi + slot) = h4;
+            *reinterpret_cast<uint4*>(my_lo + slot) = l4;
+          }
+          fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
+            tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
+            tma_store_commit();
+          }
+          (void)sub_w;
+        }
+      } else {   // kOutF32Rows
         const int oy = ty * p.TH + row / p.TW;
         const int ox = tx * p.TW + row % p.TW;
         const bool valid = (oy < p.Ho) && (ox < p.Wo);
         const long long pix = (static_cast<long long>(img) * p.Ho + oy) * p.Wo + ox;
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN; c0 += 64) {
-          if (p.out_mode == kOutSplitNHWC && n0 + c0 >= p.Cout) break;
           uint32_t r[32], rx[32];
           tmem_ld_32x32(taddr + c0, r);
           tmem_ld_32x32(taddr + BN + c0, rx);
           tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), __ldg(p.scale + n0 + c0 + j), __ldg(p.shift + n0 + c0 + j));
           if (!valid) continue;
-          if (p.out_mode == kOutSplitNHWC) {
-            const long long off = pix * p.Cout + n0 + c0;
-            if (p.res != nullptr) {
-              const uint4* rh = reinterpret_cast<const uint4*>(p.res + off);
-              const uint4* rl = reinterpret_cast<const uint4*>(p.res + p.res_plane + off);
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldc + n0 + c0);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 h4 = __ldg(rh + g), l4 = __ldg(rl + g);
-                const __half2* hh = reinterpret_cast<const __half2*>(&h4);
-                const __half2* ll = reinterpret_cast<const __half2*>(&l4);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
-                  v[g * 8 + e * 2 + 0] += fh.x + fl.x;
-                  v[g * 8 + e * 2 + 1] += fh.y + fl.y;
-                }
-              }
-            }
-            __half* oh = reinterpret_cast<__half*>(p.out) + off;
-            __half* ol = oh + p.out_plane;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 h4, l4;
-              __half2* hh = reinterpret_cast<__half2*>(&h4);
-              __half2* ll = reinterpret_cast<__half2*>(&l4);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float a = v[g * 8 + e * 2], b = v[g * 8 + e * 2 + 1];
-                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                const __half2 h2 = __floats2half2_rn(a, b);          // one cvt.rn.f16x2.f32
-                const float2 hf = __half22float2(h2);
-                hh[e] = h2;
-                ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
-              }
-              reinterpret_cast<uint4*>(oh)[g] = h4;
-              reinterpret_cast<uint4*>(ol)[g] = l4;
-            }
-          } else {   // kOutF32Rows
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldc + n0 + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 f = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-              if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
-              o[g] = f;
-            }
+          for (int g = 0; g < 8; ++g) {
+            float4 f;
+            f.x = fmaf(__uint_as_float(r[4 * g + 0]) + __uint_as_float(rx[4 * g + 0]), __ldg(p.scale + n0 + c0 + 4 * g + 0), __ldg(p.shift + n0 + c0 + 4 * g + 0));
+            f.y = fmaf(__uint_as_float(r[4 * g + 1]) + __uint_as_float(rx[4 * g + 1]), __ldg(p.scale + n0 + c0 + 4 * g + 1), __ldg(p.shift + n0 + c0 + 4 * g + 1));
+            f.z = fmaf(__uint_as_float(r[4 * g + 2]) + __uint_as_float(rx[4 * g + 2]), __ldg(p.scale + n0 + c0 + 4 * g + 2), __ldg(p.shift + n0 + c0 + 4 * g + 2));
+            f.w = fmaf(__uint_as_float(r[4 * g + 3]) + __uint_as_float(rx[4 * g + 3]), __ldg(p.scale + n0 + c0 + 4 * g + 3), __ldg(p.shift + n0 + c0 + 4 * g + 3));
+            if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+            o[g] = f;
           }
         }
       }
@@ -308,6 +367,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();     // bulk stores must complete before the CTA's shared memory goes away
   }
 
   tc_fence_before();

@@ -121,6 +121,21 @@ int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c,
   if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
   return DC_OK;
 }
+// Output (split NHWC) map for the epilogue's TMA stores: box = 32 channels x the 32-pixel sub-rectangle
+// one epilogue warp owns, SWIZZLE_64B to match the staging tile.
+int encode_out_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw) {
+  const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, 2};
+  const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
+                                 (cuuint64_t)n * h * w * c * 2};
+  const int bw = tw < 32 ? tw : 32;
+  const cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+  return DC_OK;
+}
 int encode_w_map(CUtensorMap* m, const void* base, int rows, long long K, int bn) {
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
   const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows * K * 2};
@@ -134,10 +149,10 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, long long K, int bn
 }
 
 template <int BN>
-int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const dc::ConvParams& p, cudaStream_t st) {
+int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st) {
   const int tiles = p.n_tiles_m * p.n_tiles_n;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  dc::conv_igemm_kernel<BN><<<grid, dc::kConvThreads, dc::ConvCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  dc::conv_igemm_kernel<BN><<<grid, dc::kConvThreads, dc::ConvCfg<BN>::kSmemBytes, st>>>(ta, tb, to, p);
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
@@ -397,12 +412,17 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.out_mode = a->out_f32_rows == 2 ? dc::kOutF32RowsT : (a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC);
   p.swap_ab = a->out_f32_rows == 2;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
+  memset(&to, 0, sizeof(to));
   if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH)) return rc;
+  if (!a->out_f32_rows) {
+    // output geometry as the kernel indexes it (flattened for 1x1): [n][out_h][out_w][cout]
+    if (int rc = encode_out_map(&to, a->out, n, out_h, out_w, a->cout, p.TW)) return rc;
+  }
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, bn)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 128) return launch_conv<128>(ta, tb, p, st);
-  return launch_conv<64>(ta, tb, p, st);
+  if (bn == 128) return launch_conv<128>(ta, tb, to, p, st);
+  return launch_conv<64>(ta, tb, to, p, st);
 }
 
 // ------------------------------------------------------------------ HBM kernels
@@ -449,8 +469,8 @@ int dc_head_finish(const float* col, long long ldcol, int col_off, const float* 
                    float* out, int n, int cout, int h, int w, int ho, int wo, int sigmoid, void* stream) {
   if (int rc = ensure_init()) return rc;
   if (!col || !skip || !out) return fail(DC_ERR_INVALID, "dc_head_finish: null argument");
-  const long long total = static_cast<long long>(n) * cout * ho * wo;
-  dc::head_finish_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const dim3 grid(static_cast<unsigned>(n) * cout, static_cast<unsigned>((ho * wo + 1023) / 1024));
+  dc::head_finish_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       col, ldcol, col_off, skip, ldskip, skip_off, out, n, cout, h, w, ho, wo, sigmoid);
   g_launches++;
   DC_CUDA(cudaGetLastError());

@@ -180,19 +180,21 @@ __global__ void __launch_bounds__(256) subsample_split_kernel(const __half* __re
 // (crop_layer.cu:9-38) + Eltwise SUM (eltwise_layer.cu:47-53) + Sigmoid (sigmoid_layer.cu:8-24).
 // One thread per output element, x fastest: every read and the write are unit- or 2-strided rows.
 // ---------------------------------------------------------------------------------------
+// grid = (N * Cout, ceil(Ho*Wo / 1024)); a thread handles 4 pixels of one (n, co) plane, 32-bit index math.
 __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ col, long long ldcol, int col_row0,
                                                           const float* __restrict__ skip, long long ldskip, int skip_row0,
                                                           float* __restrict__ out, int N, int Cout, int h, int w,
                                                           int Ho, int Wo, int do_sigmoid) {
-  const long long total = static_cast<long long>(N) * Cout * Ho * Wo;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(i % Wo);
-    long long r = i / Wo;
-    const int y = static_cast<int>(r % Ho);
-    r /= Ho;
-    const int co = static_cast<int>(r % Cout);
-    const int n = static_cast<int>(r / Cout);
+  const int n = blockIdx.x / Cout, co = blockIdx.x % Cout;
+  const int plane = Ho * Wo;
+  const float* crow = col + (static_cast<long long>(col_row0) + co * 9) * ldcol + static_cast<long long>(n) * h * w;
+  const float* srow = skip + (static_cast<long long>(skip_row0) + co) * ldskip + static_cast<long long>(n) * plane;
+  float* orow = out + (static_cast<long long>(n) * Cout + co) * plane;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = blockIdx.y * 1024 + it * 256 + threadIdx.x;
+    if (idx >= plane) break;
+    const int y = idx / Wo, x = idx - y * Wo;
     float up = 0.f;
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
@@ -202,14 +204,12 @@ __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restric
       for (int q = 0; q < 3; ++q) {
         const int xx = x - q;
         if (xx < 0 || (xx & 1) || (xx >> 1) >= w) continue;
-        const long long pix = (static_cast<long long>(n) * h + (yy >> 1)) * w + (xx >> 1);
-        up += __ldg(col + (col_row0 + co * 9 + p * 3 + q) * ldcol + pix);
+        up += __ldg(crow + (p * 3 + q) * ldcol + (yy >> 1) * w + (xx >> 1));
       }
     }
-    const long long opix = (static_cast<long long>(n) * Ho + y) * Wo + x;
-    float v = __ldg(skip + (skip_row0 + co) * ldskip + opix) + up;
+    float v = __ldg(srow + idx) + up;
     if (do_sigmoid) v = 1.f / (1.f + expf(-v));
-    out[i] = v;
+    orow[idx] = v;
   }
 }
 
