@@ -51,6 +51,7 @@ class Blob {
   const Dtype* gpu_diff() const;
   Dtype* mutable_cpu_data();
   Dtype* mutable_gpu_data();
+  Dtype* overwrite_gpu_data() { CHECK(data_); return static_cast<Dtype*>(data_->overwrite_gpu_data()); }
   Dtype* mutable_cpu_diff();
   Dtype* mutable_gpu_diff();
   void FromProto(const BlobProto& proto, bool reshape = true);

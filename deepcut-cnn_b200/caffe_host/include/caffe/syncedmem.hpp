@@ -20,6 +20,11 @@ class SyncedMemory {
   void set_gpu_data(void* data);
   void* mutable_cpu_data();
   void* mutable_gpu_data();
+  // Device pointer for a consumer that overwrites every element: allocates if needed and moves the
+  // head to the GPU WITHOUT uploading a host copy first.  (mutable_gpu_data() keeps the reference's
+  // semantics, syncedmem.cpp:61-69,124-132: a blob the host has read is re-uploaded before a layer
+  // writes its top -- 335 MB of pointless H2D per forward for next_pred at 16x720p.)
+  void* overwrite_gpu_data();
   enum SyncedHead { UNINITIALIZED, HEAD_AT_CPU, HEAD_AT_GPU, SYNCED };
   SyncedHead head() { return head_; }
   size_t size() { return size_; }

@@ -646,13 +646,13 @@ void FusedPlan::Run() {
       case Step::kHeadFinish: {
         Blob<float>* ob = net.blobs()[st->out_blob].get();
         DC_CHECK(dc_head_finish(static_cast<const float*>(st->col->ptr), st->col->ld, st->col_off, static_cast<const float*>(st->in2->ptr),
-                                st->in2->ld, st->skip_off, ob->mutable_gpu_data(), st->in->n, st->cout, st->in->h, st->in->w, ob->height(),
+                                st->in2->ld, st->skip_off, ob->overwrite_gpu_data(), st->in->n, st->cout, st->in->h, st->in->w, ob->height(),
                                 ob->width(), st->sigmoid, stream));
         break;
       }
       case Step::kToBlob: {
         Blob<float>* ob = net.blobs()[st->out_blob].get();
-        DC_CHECK(dc_split_to_nchw(st->in->ptr, st->in->n, st->in->c, st->in->h, st->in->w, ob->mutable_gpu_data(), stream));
+        DC_CHECK(dc_split_to_nchw(st->in->ptr, st->in->n, st->in->c, st->in->h, st->in->w, ob->overwrite_gpu_data(), stream));
         break;
       }
     }

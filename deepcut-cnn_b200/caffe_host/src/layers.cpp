@@ -19,6 +19,11 @@ void PackedWeights::Release() {
 }
 
 namespace {
+// Device pointer of a top blob every element of which the layer writes: skips the reference's
+// upload-before-write unless the layer runs in place (then the bottom's data must survive).
+float* TopPtr(Blob<float>* top, const Blob<float>* bottom) {
+  return top == bottom ? top->mutable_gpu_data() : top->overwrite_gpu_data();
+}
 // scratch device buffer per thread for the per-layer conv path (split-NHWC staging)
 struct Scratch {
   void* p = nullptr;
@@ -144,7 +149,7 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
       DC_CHECK(dc_conv_direct_nchw(reinterpret_cast<const float*>(bottom[i]->gpu_data()), reinterpret_cast<const float*>(this->blobs_[0]->gpu_data()), bias,
                                    this->num_, this->channels_, this->height_, this->width_, this->num_output_, this->kernel_h_, this->kernel_w_,
                                    this->stride_h_, this->stride_w_, this->pad_h_, this->pad_w_, this->dilation_h_, this->dilation_w_,
-                                   reinterpret_cast<float*>(top[i]->mutable_gpu_data()), st));
+                                   TopPtr(top[i], bottom[i]), st));
     return;
   }
   PackedWeights& pk = this->packed_;
@@ -183,7 +188,7 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
     a.cout = this->num_output_; a.kh = this->kernel_h_; a.kw = this->kernel_w_; a.pad = this->pad_h_; a.dilation = this->dilation_h_;
     a.w_packed = pk.w; a.scale = pk.scale; a.shift = pk.shift; a.out = ys;
     DC_CHECK(dc_conv_forward(&a, st));
-    DC_CHECK(dc_split_to_nchw(ys, this->num_, this->num_output_, this->out_h_, this->out_w_, reinterpret_cast<float*>(top[i]->mutable_gpu_data()), st));
+    DC_CHECK(dc_split_to_nchw(ys, this->num_, this->num_output_, this->out_h_, this->out_w_, TopPtr(top[i], bottom[i]), st));
   }
 }
 
@@ -194,7 +199,7 @@ void DeconvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, 
     DC_CHECK(dc_deconv_direct_nchw(reinterpret_cast<const float*>(bottom[i]->gpu_data()), reinterpret_cast<const float*>(this->blobs_[0]->gpu_data()), bias,
                                    this->num_, this->channels_, this->height_, this->width_, this->num_output_, this->kernel_h_, this->kernel_w_,
                                    this->stride_h_, this->stride_w_, this->pad_h_, this->pad_w_, this->dilation_h_, this->dilation_w_,
-                                   reinterpret_cast<float*>(top[i]->mutable_gpu_data()), Caffe::stream()));
+                                   TopPtr(top[i], bottom[i]), Caffe::stream()));
 }
 
 // ===================================================================== BatchNorm
@@ -246,7 +251,7 @@ void BatchNormLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, cons
   const int hw = bottom[0]->count() / (n * channels_);
   DC_CHECK(dc_bn_forward_nchw(reinterpret_cast<const float*>(bottom[0]->gpu_data()), reinterpret_cast<const float*>(mean_.gpu_data()),
                               reinterpret_cast<const float*>(inv_std_.gpu_data()), n, channels_, hw,
-                              reinterpret_cast<float*>(top[0]->mutable_gpu_data()), Caffe::stream()));
+                              TopPtr(top[0], bottom[0]), Caffe::stream()));
 }
 
 // ===================================================================== Scale (+bias)
@@ -294,19 +299,19 @@ template <typename Dtype>
 void ScaleLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
   DC_CHECK(dc_scale_forward_nchw(reinterpret_cast<const float*>(bottom[0]->gpu_data()), reinterpret_cast<const float*>(this->blobs_[0]->gpu_data()),
                                  bias_term_ ? reinterpret_cast<const float*>(this->blobs_[1]->gpu_data()) : nullptr, outer_dim_, scale_dim_,
-                                 inner_dim_, reinterpret_cast<float*>(top[0]->mutable_gpu_data()), Caffe::stream()));
+                                 inner_dim_, TopPtr(top[0], bottom[0]), Caffe::stream()));
 }
 
 // ===================================================================== ReLU / Sigmoid
 template <typename Dtype>
 void ReLULayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
   DC_CHECK(dc_relu_forward(reinterpret_cast<const float*>(bottom[0]->gpu_data()), bottom[0]->count(), this->layer_param_.relu_param().negative_slope(),
-                           reinterpret_cast<float*>(top[0]->mutable_gpu_data()), Caffe::stream()));
+                           TopPtr(top[0], bottom[0]), Caffe::stream()));
 }
 template <typename Dtype>
 void SigmoidLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
   DC_CHECK(dc_sigmoid_forward(reinterpret_cast<const float*>(bottom[0]->gpu_data()), bottom[0]->count(),
-                              reinterpret_cast<float*>(top[0]->mutable_gpu_data()), Caffe::stream()));
+                              TopPtr(top[0], bottom[0]), Caffe::stream()));
 }
 
 // ===================================================================== Eltwise
@@ -327,7 +332,7 @@ void EltwiseLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const vect
 }
 template <typename Dtype>
 void EltwiseLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
-  float* y = reinterpret_cast<float*>(top[0]->mutable_gpu_data());
+  float* y = (top[0] == bottom[0] || top[0] == bottom[1]) ? top[0]->mutable_gpu_data() : top[0]->overwrite_gpu_data();
   DC_CHECK(dc_axpby_forward(reinterpret_cast<const float*>(bottom[0]->gpu_data()), coeffs_[0], reinterpret_cast<const float*>(bottom[1]->gpu_data()),
                             coeffs_[1], top[0]->count(), y, Caffe::stream()));
   for (size_t i = 2; i < bottom.size(); ++i)
@@ -379,7 +384,7 @@ template <typename Dtype>
 void PoolingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
   DC_CHECK(dc_maxpool_forward_nchw(reinterpret_cast<const float*>(bottom[0]->gpu_data()), bottom[0]->num(), channels_, height_, width_, kernel_h_, kernel_w_,
                                    stride_h_, stride_w_, pad_h_, pad_w_, pooled_height_, pooled_width_,
-                                   reinterpret_cast<float*>(top[0]->mutable_gpu_data()), Caffe::stream()));
+                                   TopPtr(top[0], bottom[0]), Caffe::stream()));
 }
 
 // ===================================================================== Crop (DeepCut's)
@@ -402,7 +407,7 @@ template <typename Dtype>
 void CropLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
   DC_CHECK(dc_crop_forward_nchw(reinterpret_cast<const float*>(bottom[0]->gpu_data()), bottom[0]->num(), bottom[0]->channels(), bottom[0]->height(),
                                 bottom[0]->width(), crop_h_, crop_w_, top[0]->height(), top[0]->width(),
-                                reinterpret_cast<float*>(top[0]->mutable_gpu_data()), Caffe::stream()));
+                                TopPtr(top[0], bottom[0]), Caffe::stream()));
 }
 
 // ===================================================================== Split

@@ -97,6 +97,16 @@ void SyncedMemory::set_gpu_data(void* data) {
 void* SyncedMemory::mutable_cpu_data() { to_cpu(); head_ = HEAD_AT_CPU; ++host_epoch_; return cpu_ptr_; }
 void* SyncedMemory::mutable_gpu_data() { to_gpu(); head_ = HEAD_AT_GPU; return gpu_ptr_; }
 
+void* SyncedMemory::overwrite_gpu_data() {
+  if (gpu_ptr_ == nullptr) {
+    DC_CHECK(dc_malloc(&gpu_ptr_, size_ ? size_ : 1));
+    gpu_device_ = Caffe::device();
+    own_gpu_data_ = true;
+  }
+  head_ = HEAD_AT_GPU;
+  return gpu_ptr_;
+}
+
 void SyncedMemory::async_gpu_push(void* stream) {
   CHECK(head_ == HEAD_AT_CPU);
   if (gpu_ptr_ == nullptr) {

@@ -79,6 +79,32 @@ class _BlobArray(np.ndarray):
         self._blob = getattr(obj, "_blob", None)
 
 
+class _Outputs(dict):
+    """{blob name: array} whose arrays are taken from Blob.data on first access.  pycaffe returns
+    eager `.data` views (pycaffe.py:106-108), which forces a device->host copy of EVERY output each
+    forward -- 335 MB for the 364-channel next_pred the DeeperCut demo never reads
+    (estimate_pose.py:231).  Same mapping, fetched lazily."""
+    def __init__(self, net, names):
+        dict.__init__(self, ((n, None) for n in names))
+        self._net = net
+
+    def __getitem__(self, k):
+        v = dict.__getitem__(self, k)
+        if v is None:
+            v = self._net.blobs[k].data
+            dict.__setitem__(self, k, v)
+        return v
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+    def values(self):
+        return [self[k] for k in self]
+
+
 class Layer(object):
     def __init__(self, net, index):
         self._net = net
@@ -189,7 +215,7 @@ class Net(object):
                 end_ind = self._layer_names.index(end)
                 outputs = set([end] + blobs)
             self._forward(start_ind, end_ind)
-        return {out: self.blobs[out].data for out in outputs}
+        return _Outputs(self, sorted(outputs))
 
     def reshape(self):
         check(lib.caffe_net_reshape(self._h))
