@@ -197,6 +197,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;       // which of the two warps of this quarter
     const int row = q * 32 + lane;          // accumulator row (TMEM lane) this thread owns
+    // residual prefetch registers (split-NHWC mode): 4 rows x {hi, lo} x 16 B of the NEXT chunk
+    uint4 res_h[4], res_l[4];
+    auto prefetch_residual = [&](int t, int c0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0); }
+      if (t >= total_tiles) return;
+      const int t_nt = t % p.n_tiles_n;
+      int t_mt = t / p.n_tiles_n;
+      const int t_tx = t_mt % p.tiles_x;
+      t_mt /= p.tiles_x;
+      const int t_ty = t_mt % p.tiles_y;
+      const int t_img = t_mt / p.tiles_y;
+      if (t_nt * BN + c0 >= p.Cout) return;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = q * 32 + (lane >> 2) + 8 * i;
+        const int yy = t_ty * p.TH + rr / p.TW, xx = t_tx * p.TW + rr % p.TW;
+        if (yy < p.Ho && xx < p.Wo) {
+          const __half* src = p.res + ((static_cast<long long>(t_img) * p.Ho + yy) * p.Wo + xx) * p.Cout + t_nt * BN + c0 + (lane & 3) * 8;
+          res_h[i] = __ldg(reinterpret_cast<const uint4*>(src));
+          res_l[i] = __ldg(reinterpret_cast<const uint4*>(src + p.res_plane));
+        }
+      }
+    };
+    if (p.out_mode == kOutSplitNHWC && p.res != nullptr) prefetch_residual(blockIdx.x, half * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -244,21 +269,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // Coalesced path: the warp's 32 pixels x 32 channels chunk is staged in shared memory in the
         // TMA SWIZZLE_64B layout ([row][64 B], 16-byte piece index ^= (row >> 1) & 3, which is also
         // bank-conflict free for both access patterns below).  The residual is fetched cooperatively
-        // (lane -> 16 B piece (lane & 3) of rows (lane >> 2) + 8 i: full 32 B sectors), the result
-        // leaves through two TMA bulk-tensor stores (hi and lo plane) that clip ragged tile edges.
+        // (lane -> 16 B piece (lane & 3) of rows (lane >> 2) + 8 i: full 32 B sectors) ONE CHUNK AHEAD
+        // (registers res_h/res_l, loaded while the previous chunk is converted and stored and while the
+        // next accumulator is still being computed); the result leaves through two TMA bulk-tensor
+        // stores (hi and lo plane) that clip ragged tile edges.
         uint8_t* stg = staging_all + (warp - 2) * 4096;
-        const int sub_w = p.TW < 32 ? p.TW : 32;           // the warp's 32 rows form a sub_w x (32/sub_w) box
         const int r0 = q * 32;
         const int box_x = tx * p.TW + r0 % p.TW, box_y = ty * p.TH + r0 / p.TW;
-        long long coop_off[4];
-        bool coop_ok[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = r0 + (lane >> 2) + 8 * i;
-          const int yy = ty * p.TH + rr / p.TW, xx = tx * p.TW + rr % p.TW;
-          coop_ok[i] = (yy < p.Ho) && (xx < p.Wo);
-          coop_off[i] = ((static_cast<long long>(img) * p.Ho + yy) * p.Wo + xx) * p.Cout;
-        }
         const int piece = lane & 3;
         const int own_sw = (lane >> 1) & 3;                // swizzle of this thread's own row (row index == lane)
 #pragma unroll 1
@@ -270,31 +287,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0) tma_store_wait_read();            // previous chunk's stores have drained the staging tile
           __syncwarp();
           if (p.res != nullptr) {
-            uint4 hv[4], lv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              hv[i] = make_uint4(0, 0, 0, 0);
-              lv[i] = make_uint4(0, 0, 0, 0);
-              if (coop_ok[i]) {
-                const __half* src = p.res + coop_off[i] + n0 + c0 + piece * 8;
-                hv[i] = __ldg(reinterpret_cast<const uint4*>(src));
-                lv[i] = __ldg(reinterpret_cast<const uint4*>(src + p.res_plane));
-              }
-            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = (lane >> 2) + 8 * i;
               const int sw = (rr >> 1) & 3;
-              *reinterpret_cast<uint4*>(stg + rr * 64 + ((piece ^ sw) << 4)) = hv[i];
-              *reinterpret_cast<uint4*>(stg + 2048 + rr * 64 + ((piece ^ sw) << 4)) = lv[i];
+              *reinterpret_cast<uint4*>(stg + rr * 64 + ((piece ^ sw) << 4)) = res_h[i];
+              *reinterpret_cast<uint4*>(stg + 2048 + rr * 64 + ((piece ^ sw) << 4)) = res_l[i];
             }
             __syncwarp();
+            // prefetch the residual of the chunk this warp handles next (same tile, or the next tile's first)
+            int ntile = tile, nc0 = c0 + 64;
+            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { ntile = tile + gridDim.x; nc0 = half * 32; }
+            prefetch_residual(ntile, nc0);
+          }
+          float sc[32], sh[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0) + g);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c0) + g);
+            sc[4 * g] = a4.x; sc[4 * g + 1] = a4.y; sc[4 * g + 2] = a4.z; sc[4 * g + 3] = a4.w;
+            sh[4 * g] = b4.x; sh[4 * g + 1] = b4.y; sh[4 * g + 2] = b4.z; sh[4 * g + 3] = b4.w;
           }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), __ldg(p.scale + n0 + c0 + j), __ldg(p.shift + n0 + c0 + j));
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), sc[j], sh[j]);
           uint8_t* my_hi = stg + lane * 64;
           uint8_t* my_lo = my_hi + 2048;
 #pragma unroll
@@ -334,7 +351,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
             tma_store_commit();
           }
-          (void)sub_w;
         }
       } else {   // kOutF32Rows
         const int oy = ty * p.TH + row / p.TW;
