@@ -61,23 +61,33 @@ struct ConvParams {
   int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
 };
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2 MMA with M = 256)
+// computes two vertically adjacent 128-pixel tiles against the same BN channels; each CTA stages its
+// own 128 A rows but only BN/2 rows of B, so the bytes every SM pulls from L2 per MMA drop by 25 %
+// (64 KB -> 48 KB per K-chunk) and a fourth pipeline stage fits in shared memory.
+template <int BN, int CG = 1>
 struct ConvCfg {
   static constexpr int kABytes = kBM * kBK * 2;          // one plane of A per stage
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBRows = BN / CG;                 // B rows resident in THIS CTA
+  static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static_assert(BN == 64 || BN == 128, "4 accumulators of BN columns must fit 512 TMEM columns");
-  static constexpr int kStages = (BN >= 128 ? 3 : 4);
+  static constexpr int kStages = CG == 2 ? 4 : (BN >= 128 ? 3 : 4);
   static constexpr int kTmemCols = 4 * BN;                         // 2 x (main, cross)
   static constexpr int kStagingBytes = 8 * 4096;         // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo}
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, CG>;
+  const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  // work units: (m-tile group of CG tiles, n-tile); unit u -> n-tile u % n_tiles_n, m-tile CG * (u / n_tiles_n) + rank
+  const int unit_first = CG == 2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int unit_stride = CG == 2 ? (gridDim.x >> 1) : gridDim.x;
+  const int total_units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -92,7 +102,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   const int kchunks = p.Cin / kBK;
   const int ksteps = p.ntaps * kchunks;
 
@@ -106,13 +115,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&tempty_bar[a], 8 * CG);      // every epilogue warp of every CTA of the group
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();             // peer barriers are initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -121,25 +134,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
+      for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+        const int nt = unit % p.n_tiles_n;
+        int mt = (unit / p.n_tiles_n) * CG + cta_rank;    // a phantom tile (mt == n_tiles_m) decodes to img == N: all-OOB boxes
         const int tx = mt % p.tiles_x;
         mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
         const int img = mt / p.tiles_y;
-        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN;
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN + cta_rank * Cfg::kBRows;
         for (int t = 0; t < p.ntaps; ++t) {
           const int ix = x0 + p.tap_dx[t], iy = y0 + p.tap_dy[t];
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
-            tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
             const int kcoord = (t * kchunks + kc) * kBK;
-            tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
-            tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+            if (CG == 2) {
+              // both CTAs' loads count on the leader's barrier; only the leader arms it (for both halves)
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
+              tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
+              tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
+              tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+            } else {
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
+              tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
+              tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
+              tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -147,13 +169,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+    if (lane == 0 && cta_rank == 0) {             // the leader CTA issues for the whole group
+      constexpr uint32_t idesc = umma_idesc_f16(kBM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = unit_first; unit < total_units; unit += unit_stride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 2 * BN);   // main
@@ -171,7 +193,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);   // 16 fp16 = 32 B along K
             // hi*hi, hi*lo and lo*hi are symmetric in (A, B): swapping the operands only transposes D
-            if (p.swap_ab) {
+            if (CG == 2) {
+              umma_f16_2cta(d, a_hi + adv, b_hi + adv, idesc, accum);
+              umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, accum);
+              accum = 1;
+              umma_f16_2cta(dx, a_lo + adv, b_hi + adv, idesc, 1);
+            } else if (p.swap_ab) {
               umma_f16(d, b_hi + adv, a_hi + adv, idesc, accum);
               umma_f16(dx, b_hi + adv, a_lo + adv, idesc, accum);
               accum = 1;
@@ -183,10 +210,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               umma_f16(dx, a_lo + adv, b_hi + adv, idesc, 1);
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if (CG == 2) umma_commit_2cta(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (CG == 2) umma_commit_2cta(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -199,12 +228,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = q * 32 + lane;          // accumulator row (TMEM lane) this thread owns
     // residual prefetch registers (split-NHWC mode): 4 rows x {hi, lo} x 16 B of the NEXT chunk
     uint4 res_h[4], res_l[4];
-    auto prefetch_residual = [&](int t, int c0) {
+    auto prefetch_residual = [&](int u, int c0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0); }
-      if (t >= total_tiles) return;
-      const int t_nt = t % p.n_tiles_n;
-      int t_mt = t / p.n_tiles_n;
+      if (u >= total_units) return;
+      const int t_nt = u % p.n_tiles_n;
+      int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
+      if (t_mt >= p.n_tiles_m) return;
       const int t_tx = t_mt % p.tiles_x;
       t_mt /= p.tiles_x;
       const int t_ty = t_mt % p.tiles_y;
@@ -221,12 +251,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     };
-    if (p.out_mode == kOutSplitNHWC && p.res != nullptr) prefetch_residual(blockIdx.x, half * 32);
+    if (p.out_mode == kOutSplitNHWC && p.res != nullptr) prefetch_residual(unit_first, half * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles_n;
-      int mt = tile / p.n_tiles_n;
+    for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+      const int nt = unit % p.n_tiles_n;
+      int mt = (unit / p.n_tiles_n) * CG + cta_rank;
+      const bool tile_ok = mt < p.n_tiles_m;       // the odd CTA of the last pair may own a phantom tile
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
@@ -296,9 +327,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             __syncwarp();
             // prefetch the residual of the chunk this warp handles next (same tile, or the next tile's first)
-            int ntile = tile, nc0 = c0 + 64;
-            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { ntile = tile + gridDim.x; nc0 = half * 32; }
-            prefetch_residual(ntile, nc0);
+            int nunit = unit, nc0 = c0 + 64;
+            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { nunit = unit + unit_stride; nc0 = half * 32; }
+            prefetch_residual(nunit, nc0);
           }
           float sc[32], sh[32];
 #pragma unroll
@@ -355,7 +386,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else {   // kOutF32Rows
         const int oy = ty * p.TH + row / p.TW;
         const int ox = tx * p.TW + row % p.TW;
-        const bool valid = (oy < p.Ho) && (ox < p.Wo);
+        const bool valid = tile_ok && (oy < p.Ho) && (ox < p.Wo);
         const long long pix = (static_cast<long long>(img) * p.Ho + oy) * p.Wo + ox;
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN; c0 += 64) {
@@ -379,7 +410,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -387,10 +421,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();             // nobody touches the peer's barriers / TMEM after this
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CG == 2) tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

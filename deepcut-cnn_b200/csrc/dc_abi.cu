@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -148,14 +149,38 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, long long K, int bn
   return DC_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st) {
-  const int tiles = p.n_tiles_m * p.n_tiles_n;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  dc::conv_igemm_kernel<BN><<<grid, dc::kConvThreads, dc::ConvCfg<BN>::kSmemBytes, st>>>(ta, tb, to, p);
+  const int units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
+  int grid = units * CG < g_num_sms ? units * CG : g_num_sms;
+  if (CG == 2) grid &= ~1;
+  if (CG == 1) {
+    dc::conv_igemm_kernel<BN, 1><<<grid, dc::kConvThreads, dc::ConvCfg<BN, 1>::kSmemBytes, st>>>(ta, tb, to, p);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(dc::kConvThreads);
+    cfg.dynamicSmemBytes = dc::ConvCfg<BN, 2>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, 2>, ta, tb, to, p));
+  }
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
+}
+
+// CTA-pair (cta_group::2) kernels for the pixel-major modes; DC_CONV_2CTA=0 falls back to single CTAs.
+bool use_2cta() {
+  static const bool on = [] { const char* e = getenv("DC_CONV_2CTA"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int ew_grid(long long total) {
@@ -201,8 +226,10 @@ int dc_init(int device) {
     if (!fn || q != cudaDriverEntryPointSuccess) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128>::kSmemBytes));
-  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 1>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 1>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 2>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::kC1SmemFloats * 4));
   g_inited = true;
   return DC_OK;
@@ -419,10 +446,12 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
     // output geometry as the kernel indexes it (flattened for 1x1): [n][out_h][out_w][cout]
     if (int rc = encode_out_map(&to, a->out, n, out_h, out_w, a->cout, p.TW)) return rc;
   }
-  if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, bn)) return rc;
+  const bool pair_mode = use_2cta() && a->out_f32_rows != 2 && g_num_sms >= 2;
+  if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair_mode ? bn / 2 : bn)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 128) return launch_conv<128>(ta, tb, to, p, st);
-  return launch_conv<64>(ta, tb, to, p, st);
+  const bool pair = use_2cta() && !p.swap_ab && g_num_sms >= 2;
+  if (bn == 128) return pair ? launch_conv<128, 2>(ta, tb, to, p, st) : launch_conv<128, 1>(ta, tb, to, p, st);
+  return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
 }
 
 // ------------------------------------------------------------------ HBM kernels

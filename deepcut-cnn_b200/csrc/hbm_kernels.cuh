@@ -20,7 +20,7 @@ constexpr int kC1PatchH = kC1TileH * 2 + 5, kC1PatchW = kC1TileW * 2 + 5;   // 2
 constexpr int kC1PatchWPad = kC1PatchW + 2;                                 // 71: odd stride, no 2-way conflicts
 constexpr int kC1SmemFloats = 147 * 64 + 3 * kC1PatchH * kC1PatchWPad;
 
-__global__ void __launch_bounds__(256) conv1_7x7s2_kernel(const float* __restrict__ x, const float* __restrict__ wk,
+__global__ void __launch_bounds__(256, 2) conv1_7x7s2_kernel(const float* __restrict__ x, const float* __restrict__ wk,
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift, __half* __restrict__ out,
                                                           long long out_plane, int N, int H, int W, int Ho, int Wo) {

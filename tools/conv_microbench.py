@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmark for dc_conv_forward (tuning aid, not a bench number): times one conv
+geometry with CUDA events, optionally with the residual epilogue."""
+import argparse
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+libdc = importlib.import_module("deepcut-cnn_b200.libdc")
+L = libdc.lib()
+libdc.check(L.dc_init(0))
+
+
+def run(n, h, w, cin, cout, k, pad, dil, residual, mode, iters=20):
+    rows = L.dc_packed_rows(cout)
+    K = k * k * cin
+    x = torch.randn(2, n, h, w, cin, device="cuda").half()
+    wp = torch.randn(2, rows, K, device="cuda").half()
+    sc = torch.ones(rows, device="cuda")
+    sh = torch.zeros(rows, device="cuda")
+    ho, wo = h + 2 * pad - (dil * (k - 1) + 1) + 1, w + 2 * pad - (dil * (k - 1) + 1) + 1
+    res = torch.randn(2, n, ho, wo, cout, device="cuda").half() if residual else None
+    if mode == 0:
+        out = torch.empty(2, n, ho, wo, cout, device="cuda", dtype=torch.half)
+        ldc = 0
+    elif mode == 1:
+        out = torch.empty(n * ho * wo, rows, device="cuda")
+        ldc = rows
+    else:
+        ldc = (n * ho * wo + 31) // 32 * 32
+        out = torch.empty(rows, ldc, device="cuda")
+    a = libdc.ConvArgs(x=x.data_ptr(), n=n, h=h, w=w, cin=cin, cout=cout, kh=k, kw=k, pad=pad, dilation=dil,
+                       w_packed=wp.data_ptr(), scale=sc.data_ptr(), shift=sh.data_ptr(),
+                       residual=res.data_ptr() if residual else None, relu=1 if mode == 0 else 0, out_f32_rows=mode, ldc=ldc,
+                       out=out.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        libdc.check(L.dc_conv_forward(C.byref(a), st))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        libdc.check(L.dc_conv_forward(C.byref(a), st))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 2.0 * n * ho * wo * cout * K
+    by = 4.0 * (n * h * w * cin + n * ho * wo * cout * (2 if residual else 1))
+    print("n%d %dx%d %d->%d k%d d%d res=%d mode=%d : %.1f us  %.0f TF/s (x3 issued %.0f)  %.0f GB/s" %
+          (n, h, w, cin, cout, k, dil, residual, mode, ms * 1e3, fl / ms / 1e9, 3 * fl / ms / 1e9, by / ms / 1e6))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--set", default="res4")
+    args = ap.parse_args()
+    if args.set == "res4":
+        for res in (1, 0):
+            run(16, 45, 80, 256, 1024, 1, 0, 1, res, 0)
+        run(16, 45, 80, 256, 1024, 1, 0, 1, 0, 1)
+        run(16, 45, 80, 256, 1024, 1, 0, 1, 0, 2)
+        run(16, 45, 80, 1024, 256, 1, 0, 1, 0, 0)
+        run(16, 45, 80, 256, 256, 3, 1, 1, 0, 0)
+        run(16, 45, 80, 512, 512, 3, 2, 2, 0, 0)
+        run(16, 90, 160, 128, 512, 1, 0, 1, 1, 0)
+        run(16, 180, 320, 64, 256, 1, 0, 1, 1, 0)
