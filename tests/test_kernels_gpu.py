@@ -77,6 +77,20 @@ def test_conv_residual_add_relu(_gpu):
     assert np.abs(got2 - branch).max() < 1e-4 and (got2 < 0).any()
 
 
+def test_conv_residual_ragged_channel_tile(_gpu):
+    # cout = 192: the second 128-channel tile is half empty; residual prefetch buffers of the skipped
+    # chunks must not leak into the next tile (several pixel tiles so every CTA sees both n-tiles)
+    rng = np.random.default_rng(21)
+    n, ci, co, h, w = 2, 64, 192, 40, 37
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, 1, 1)) * np.sqrt(2.0 / ci)).astype(np.float32)
+    a, b = _bn_params(rng, co)
+    shortcut = rng.standard_normal((n, co, h, w)).astype(np.float32)
+    ref = np.maximum(caffe_ref.convolution(x, wt, None, 1, 0, 1) * a.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1) + shortcut, 0)
+    got = _gpu.conv_bn(x, wt, a, b, relu=True, residual_nchw=shortcut)
+    assert np.abs(got - ref).max() < 1e-4
+
+
 def test_conv_f32_rows_with_bias_heads(_gpu):
     # merged 1x1 heads: 512 -> 14+28+364 = 406 with bias, fp32 rows out (res3d_* layers)
     rng = np.random.default_rng(8)
