@@ -226,14 +226,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;       // which of the two warps of this quarter
     const int row = q * 32 + lane;          // accumulator row (TMEM lane) this thread owns
-    // Residual prefetch registers (split-NHWC mode): each warp owns up to two 32-channel chunks per
-    // tile; chunk j's residual (4 rows x {hi, lo} x 16 B per lane) lives in buffer j and is re-loaded
-    // for the NEXT tile as soon as it has been copied to the staging tile, so a full tile of residual
-    // per warp (64 KB per SM) is in flight while the current tile is converted and stored.
-    uint4 res_h0[4], res_l0[4], res_h1[4], res_l1[4];
-    auto prefetch_residual = [&](int u, int c0, uint4 (&rh)[4], uint4 (&rl)[4]) {
+    // residual prefetch registers (split-NHWC mode): 4 rows x {hi, lo} x 16 B of the NEXT chunk
+    uint4 res_h[4], res_l[4];
+    auto prefetch_residual = [&](int u, int c0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
+      for (int i = 0; i < 4; ++i) { res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0); }
       if (u >= total_units) return;
       const int t_nt = u % p.n_tiles_n;
       int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
@@ -242,23 +239,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       t_mt /= p.tiles_x;
       const int t_ty = t_mt % p.tiles_y;
       const int t_img = t_mt / p.tiles_y;
-      if (c0 >= BN || t_nt * BN + c0 >= p.Cout) return;
+      if (t_nt * BN + c0 >= p.Cout) return;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rr = q * 32 + (lane >> 2) + 8 * i;
         const int yy = t_ty * p.TH + rr / p.TW, xx = t_tx * p.TW + rr % p.TW;
         if (yy < p.Ho && xx < p.Wo) {
           const __half* src = p.res + ((static_cast<long long>(t_img) * p.Ho + yy) * p.Wo + xx) * p.Cout + t_nt * BN + c0 + (lane & 3) * 8;
-          rh[i] = __ldg(reinterpret_cast<const uint4*>(src));
-          rl[i] = __ldg(reinterpret_cast<const uint4*>(src + p.res_plane));
+          res_h[i] = __ldg(reinterpret_cast<const uint4*>(src));
+          res_l[i] = __ldg(reinterpret_cast<const uint4*>(src + p.res_plane));
         }
       }
     };
-    const bool has_res = p.out_mode == kOutSplitNHWC && p.res != nullptr;
-    if (has_res) {
-      prefetch_residual(unit_first, half * 32, res_h0, res_l0);
-      prefetch_residual(unit_first, half * 32 + 64, res_h1, res_l1);
-    }
+    if (p.out_mode == kOutSplitNHWC && p.res != nullptr) prefetch_residual(unit_first, half * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = unit_first; unit < total_units; unit += unit_stride) {
@@ -316,40 +309,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int box_x = tx * p.TW + r0 % p.TW, box_y = ty * p.TH + r0 / p.TW;
         const int piece = lane & 3;
         const int own_sw = (lane >> 1) & 3;                // swizzle of this thread's own row (row index == lane)
-        auto do_chunk = [&](int c0, uint4 (&rh)[4], uint4 (&rl)[4]) {
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          if (n0 + c0 >= p.Cout) {
+            // ragged last channel tile: nothing to do here, but if this was the warp's first chunk the
+            // prefetch registers still hold the zeros meant for it -- refill them for the next tile
+            if (p.res != nullptr && c0 == half * 32) prefetch_residual(unit + unit_stride, half * 32);
+            break;
+          }
           uint32_t r[32], rx[32];
           tmem_ld_32x32(taddr + c0, r);
           tmem_ld_32x32(taddr + BN + c0, rx);
           if (lane == 0) tma_store_wait_read();            // previous chunk's stores have drained the staging tile
           __syncwarp();
-          if (has_res) {
+          if (p.res != nullptr) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = (lane >> 2) + 8 * i;
               const int sw = (rr >> 1) & 3;
-              *reinterpret_cast<uint4*>(stg + rr * 64 + ((piece ^ sw) << 4)) = rh[i];
-              *reinterpret_cast<uint4*>(stg + 2048 + rr * 64 + ((piece ^ sw) << 4)) = rl[i];
+              *reinterpret_cast<uint4*>(stg + rr * 64 + ((piece ^ sw) << 4)) = res_h[i];
+              *reinterpret_cast<uint4*>(stg + 2048 + rr * 64 + ((piece ^ sw) << 4)) = res_l[i];
             }
             __syncwarp();
-            prefetch_residual(unit + unit_stride, c0, rh, rl);   // same chunk of this warp's next tile
+            // prefetch the residual of the chunk this warp handles next (same tile, or the next tile's first)
+            int nunit = unit, nc0 = c0 + 64;
+            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { nunit = unit + unit_stride; nc0 = half * 32; }
+            prefetch_residual(nunit, nc0);
+          }
+          float sc[32], sh[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0) + g);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c0) + g);
+            sc[4 * g] = a4.x; sc[4 * g + 1] = a4.y; sc[4 * g + 2] = a4.z; sc[4 * g + 3] = a4.w;
+            sh[4 * g] = b4.x; sh[4 * g + 1] = b4.y; sh[4 * g + 2] = b4.z; sh[4 * g + 3] = b4.w;
           }
           tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), sc[j], sh[j]);
           uint8_t* my_hi = stg + lane * 64;
           uint8_t* my_lo = my_hi + 2048;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int slot = (g ^ own_sw) << 4;
-            const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0) + 2 * g);
-            const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0) + 2 * g + 1);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c0) + 2 * g);
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c0) + 2 * g + 1);
-            const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              v[e] = fmaf(__uint_as_float(r[g * 8 + e]) + __uint_as_float(rx[g * 8 + e]), sc[e], sh[e]);
-            if (has_res) {
+            if (p.res != nullptr) {
               const uint4 h4 = *reinterpret_cast<const uint4*>(my_hi + slot);
               const uint4 l4 = *reinterpret_cast<const uint4*>(my_lo + slot);
               const __half2* hh = reinterpret_cast<const __half2*>(&h4);
@@ -357,8 +361,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
-                v[e * 2 + 0] += fh.x + fl.x;
-                v[e * 2 + 1] += fh.y + fl.y;
+                v[g * 8 + e * 2 + 0] += fh.x + fl.x;
+                v[g * 8 + e * 2 + 1] += fh.y + fl.y;
               }
             }
             uint4 h4, l4;
@@ -366,7 +370,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __half2* ll = reinterpret_cast<__half2*>(&l4);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = v[e * 2], b = v[e * 2 + 1];
+              float a = v[g * 8 + e * 2], b = v[g * 8 + e * 2 + 1];
               if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
               const __half2 h2 = __floats2half2_rn(a, b);
               const float2 hf = __half22float2(h2);
@@ -383,13 +387,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
             tma_store_commit();
           }
-        };
-        // a chunk beyond Cout (ragged last n-tile) is skipped, but its buffer must still be refilled for the next tile
-        if (n0 + half * 32 < p.Cout) do_chunk(half * 32, res_h0, res_l0);
-        else if (has_res) prefetch_residual(unit + unit_stride, half * 32, res_h0, res_l0);
-        if (BN > 64) {
-          if (n0 + half * 32 + 64 < p.Cout) do_chunk(half * 32 + 64, res_h1, res_l1);
-          else if (has_res) prefetch_residual(unit + unit_stride, half * 32 + 64, res_h1, res_l1);
         }
       } else {   // kOutF32Rows
         const int oy = ty * p.TH + row / p.TW;
