@@ -1,6 +1,7 @@
 #include "caffe/dc_engine.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <sstream>
@@ -15,7 +16,8 @@ typedef BaseConvolutionLayer<float> ConvBase;
 // A value flowing through the net.  In-place layers create a new Tensor on the same blob; Split
 // tops alias their bottom's Tensor.
 struct FusedPlan::Tensor {
-  enum Kind { kBlobF32, kSplit, kF32Rows, kVirtual } kind = kVirtual;
+  enum Kind { kBlobF32, kSplit, kF32Rows, kRaw, kVirtual } kind = kVirtual;
+  size_t raw_bytes = 0;               // kRaw: scratch of this many bytes
   int id = 0;
   int n = 0, c = 0, h = 0, w = 0;
   int ld = 0;                         // kF32Rows: row stride (floats); rows = n*h*w
@@ -46,6 +48,8 @@ struct FusedPlan::Step {
   // head finish
   int col_off = 0, skip_off = 0, sigmoid = 0, out_blob = -1;
   Tensor* col = nullptr;
+  Tensor* ws = nullptr;               // kConv1 (tensor-core stem): space-to-depth scratch
+  bool stem_tc = false;
   // pooling
   int pool_k = 3, pool_s = 2;
 };
@@ -177,6 +181,12 @@ struct Matcher {
       st->in = in; st->out = out; st->conv_layer = i; st->bn_layer = bn; st->scale_layer = sc; st->relu = true;
       st->cout = 64;
       out->kind = FusedPlan::Tensor::kSplit;
+      const char* e = getenv("DC_STEM_TC");
+      st->stem_tc = !(e && e[0] == '0');
+      if (st->stem_tc) {
+        st->ws = NewInternal(FusedPlan::Tensor::kRaw, in->n, 16, (in->h + 1) / 2, (in->w + 1) / 2 + 3);
+        st->ws->raw_bytes = dc_conv1_tc_workspace_bytes(in->n, in->h, in->w);
+      }
       return true;
     }
     if (in->kind != FusedPlan::Tensor::kSplit) return Fail("convolution " + lname + " input is not a split-NHWC activation");
@@ -425,6 +435,7 @@ bool FusedPlan::Match(Net<float>& net, bool materialize, std::string* why) {
 void FusedPlan::PlanMemory() {
   for (size_t s = 0; s < steps_.size(); ++s) {
     Step* st = steps_[s];
+    if (st->ws) { st->ws->def_step = static_cast<int>(s); st->ws->last_step = static_cast<int>(s); }
     Tensor* ins[3] = {st->in, st->in2, st->col};
     for (Tensor* t : ins)
       if (t) t->last_step = std::max(t->last_step, static_cast<int>(s));
@@ -474,6 +485,10 @@ void FusedPlan::PlanMemory() {
     }
   };
   for (size_t s = 0; s < steps_.size(); ++s) {
+    if (Tensor* w = steps_[s]->ws) {
+      w->bytes = w->raw_bytes;
+      w->offset = alloc(w->bytes);
+    }
     Tensor* t = steps_[s]->out;
     if (t && t->def_step == static_cast<int>(s) && (t->kind == Tensor::kSplit || t->kind == Tensor::kF32Rows)) {
       t->bytes = t->kind == Tensor::kSplit ? t->elems() * 4 : static_cast<size_t>(t->n) * t->h * t->w * t->ld * 4;
@@ -532,10 +547,19 @@ void FusedPlan::UploadWeights(Net<float>& net) {
   for (Step* st : steps_) {
     if (st->type == Step::kConv1) {
       Layer<float>* cl = net.layers()[st->conv_layer].get();
-      std::vector<float> wp(147 * 64), a, b;
-      DC_CHECK(dc_pack_conv1_weight(cl->blobs()[0]->cpu_data(), wp.data()));
+      std::vector<float> a, b;
       fold(st->bn_layer, st->scale_layer, 64, &a, &b);
-      st->w_dev = upload(wp.data(), wp.size() * 4);
+      if (st->stem_tc) {
+        std::vector<uint16_t> packed(2 * 64 * 256);
+        std::vector<float> rs(64);
+        DC_CHECK(dc_pack_conv1_tc_weight(cl->blobs()[0]->cpu_data(), packed.data(), rs.data()));
+        for (int c = 0; c < 64; ++c) a[c] *= rs[c];
+        st->w_dev = upload(packed.data(), packed.size() * 2);
+      } else {
+        std::vector<float> wp(147 * 64);
+        DC_CHECK(dc_pack_conv1_weight(cl->blobs()[0]->cpu_data(), wp.data()));
+        st->w_dev = upload(wp.data(), wp.size() * 4);
+      }
       st->scale_dev = static_cast<float*>(upload(a.data(), 64 * 4));
       st->shift_dev = static_cast<float*>(upload(b.data(), 64 * 4));
     } else if (st->type == Step::kConvBN) {
@@ -618,8 +642,12 @@ void FusedPlan::Run() {
     ++step_index;
     switch (st->type) {
       case Step::kConv1: {
-        DC_CHECK(dc_conv1_forward(blob_in(st->in), st->in->n, st->in->h, st->in->w, static_cast<const float*>(st->w_dev), st->scale_dev,
-                                  st->shift_dev, st->out->ptr, stream));
+        if (st->stem_tc)
+          DC_CHECK(dc_conv1_tc_forward(blob_in(st->in), st->in->n, st->in->h, st->in->w, st->w_dev, st->scale_dev, st->shift_dev,
+                                       st->ws->ptr, st->out->ptr, stream));
+        else
+          DC_CHECK(dc_conv1_forward(blob_in(st->in), st->in->n, st->in->h, st->in->w, static_cast<const float*>(st->w_dev), st->scale_dev,
+                                    st->shift_dev, st->out->ptr, stream));
         break;
       }
       case Step::kConvBN:

@@ -2,6 +2,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -375,6 +376,31 @@ int dc_pack_conv1_weight(const float* w, float* packed) {
   return DC_OK;
 }
 
+int dc_pack_conv1_tc_weight(const float* w, uint16_t* packed, float* rowscale) {
+  if (!w || !packed || !rowscale) return fail(DC_ERR_INVALID, "dc_pack_conv1_tc_weight: bad arguments");
+  const int K = 256;
+  std::vector<float> row(K);
+  for (int co = 0; co < 64; ++co) {
+    std::fill(row.begin(), row.end(), 0.f);
+    for (int ci = 0; ci < 3; ++ci)
+      for (int P = 0; P < 7; ++P)
+        for (int Q = 0; Q < 7; ++Q) {
+          // P - 3 = 2 t + py, t = floor((P-3)/2) in {-2..1}
+          const int dP = P - 3, dQ = Q - 3;
+          const int ty = (dP >= 0) ? dP / 2 : -((-dP + 1) / 2), py = dP - 2 * ty;
+          const int tx = (dQ >= 0) ? dQ / 2 : -((-dQ + 1) / 2), px = dQ - 2 * tx;
+          row[(ty + 2) * 64 + (tx + 2) * 16 + (py * 2 + px) * 3 + ci] = w[((co * 3 + ci) * 7 + P) * 7 + Q];
+        }
+    pack_row(K, [&](int k) { return row[k]; }, packed + static_cast<long long>(co) * K, packed + static_cast<long long>(64 + co) * K, rowscale + co);
+  }
+  return DC_OK;
+}
+
+size_t dc_conv1_tc_workspace_bytes(int n, int h, int w) {
+  const long long h2 = (h + 1) / 2, w2 = (w + 1) / 2;
+  return static_cast<size_t>(2ll * n * h2 * (w2 + 3) * 16 * 2);
+}
+
 int dc_pool_out_size(int size, int kernel, int stride) {
   // PoolingLayer::Reshape, pooling_layer.cpp:90-93 (pad 0): ceil((size - k) / s) + 1
   return static_cast<int>(std::ceil(static_cast<float>(size - kernel) / stride)) + 1;
@@ -451,6 +477,57 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool pair = use_2cta() && !p.swap_ab && g_num_sms >= 2;
   if (bn == 128) return pair ? launch_conv<128, 2>(ta, tb, to, p, st) : launch_conv<128, 1>(ta, tb, to, p, st);
+  return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
+}
+
+// ------------------------------------------------------------------ tensor-core stem
+int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packed, const float* scale,
+                        const float* shift, void* workspace, void* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!x || !w_packed || !scale || !shift || !workspace || !out) return fail(DC_ERR_INVALID, "dc_conv1_tc_forward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int h2 = (h + 1) / 2, w2 = (w + 1) / 2, wp = w2 + 3;
+  const long long plane = static_cast<long long>(n) * h2 * wp * 16;
+  dc::stem_s2d_kernel<<<ew_grid(static_cast<long long>(n) * h2 * wp), 256, 0, st>>>(x, static_cast<__half*>(workspace), plane, n, h, w, h2, w2);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+
+  dc::ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = h2; p.W = w2; p.Ho = h2; p.Wo = w2; p.Cout = 64; p.Cin = 64;
+  p.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t - 2; p.tap_dx[t] = 0; }
+  const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
+  long long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cand[i][0], th = cand[i][1];
+    const long long area = static_cast<long long>((w2 + tw - 1) / tw) * tw * ((h2 + th - 1) / th) * th;
+    if (best < 0 || area < best) { best = area; p.TW = tw; p.TH = th; }
+  }
+  p.tiles_x = (w2 + p.TW - 1) / p.TW;
+  p.tiles_y = (h2 + p.TH - 1) / p.TH;
+  p.n_tiles_m = n * p.tiles_x * p.tiles_y;
+  p.n_tiles_n = 1;
+  p.scale = scale; p.shift = shift;
+  p.out = out;
+  p.out_plane = static_cast<long long>(n) * h2 * w2 * 64;
+  p.relu = 1;
+  p.out_mode = dc::kOutSplitNHWC;
+
+  // A: overlapping 4-pixel windows of the padded space-to-depth image (W stride = one 16-channel pixel)
+  CUtensorMap ta, tb, to;
+  {
+    const cuuint64_t dims[5] = {64, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)n, 2};
+    const cuuint64_t strides[4] = {32, (cuuint64_t)wp * 32, (cuuint64_t)h2 * wp * 32, (cuuint64_t)plane * 2};
+    const cuuint32_t box[5] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, workspace, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled(stem windows) failed: %d", (int)r);
+  }
+  const bool pair = use_2cta() && g_num_sms >= 2;
+  if (int rc = encode_w_map(&tb, w_packed, 64, 256, pair ? 32 : 64)) return rc;
+  if (int rc = encode_out_map(&to, out, n, h2, w2, 64, p.TW)) return rc;
   return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
 }
 

@@ -100,6 +100,61 @@ __global__ void __launch_bounds__(256, 2) conv1_7x7s2_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------
+// Stem on tensor cores.  A 7x7 / stride-2 / pad-3 convolution over 3 channels is a 4x4 / stride-1
+// convolution over the 2x2 space-to-depth image (12 channels: c' = (py*2 + px)*3 + ci, padded to 16):
+// input row 2*oy - 3 + P = 2*(oy + t) + py with t = floor((P-3)/2) in {-2..1}.  With 16 channels per
+// pixel, FOUR horizontally adjacent pixels are 64 contiguous fp16 = one 128-byte K-chunk, so a tensor
+// map whose W stride is one pixel (32 B) but whose inner extent is four pixels (overlapping windows)
+// feeds conv_igemm directly: 4 vertical taps x K = 64.  This kernel writes that image, split fp16,
+// with 2 zero columns on the left and 1 on the right so every window is in bounds:
+//   out[plane][n][Y][X + 2][c'],  Y < ceil(H/2), X in [-2, ceil(W/2) + 1).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, __half* __restrict__ out,
+                                                       long long out_plane, int N, int H, int W, int H2, int W2) {
+  const int Wp = W2 + 3;
+  const long long total = static_cast<long long>(N) * H2 * Wp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xp = static_cast<int>(i % Wp);
+    long long r = i / Wp;
+    const int Y = static_cast<int>(r % H2);
+    const int n = static_cast<int>(r / H2);
+    const int X = xp - 2;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (X >= 0 && X < W2) {
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const int iy = 2 * Y + py;
+        if (iy >= H) continue;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float* row = x + ((static_cast<long long>(n) * 3 + ci) * H + iy) * W;
+          const int ix = 2 * X;
+          v[(py * 2 + 0) * 3 + ci] = __ldg(row + ix);
+          if (ix + 1 < W) v[(py * 2 + 1) * 3 + ci] = __ldg(row + ix + 1);
+        }
+      }
+    }
+    uint4 h4[2], l4[2];
+    __half2* hh = reinterpret_cast<__half2*>(h4);
+    __half2* ll = reinterpret_cast<__half2*>(l4);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      const float2 hf = __half22float2(h2);
+      hh[e] = h2;
+      ll[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(out + i * 16);
+    uint4* ol = reinterpret_cast<uint4*>(out + out_plane + i * 16);
+    oh[0] = h4[0]; oh[1] = h4[1];
+    ol[0] = l4[0]; ol[1] = l4[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // MAX pooling k x k / stride s, pad 0, Caffe ceil-mode output size, windows clipped at the
 // bottom/right edge (PoolingLayer::Forward_gpu pooling_layer.cu:10-47).  One thread = one
 // output pixel x 8 channels (128-bit loads of hi and lo).  The winner's (hi, lo) pair is

@@ -45,6 +45,10 @@ _SIGS = {
     "dc_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "dc_conv1_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "dc_conv1_tc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dc_pack_conv1_tc_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dc_conv1_tc_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "dc_maxpool_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p]),
     "dc_pool_out_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),

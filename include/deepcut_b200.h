@@ -121,6 +121,16 @@ int dc_conv_forward(const dc_conv_args* args, void* stream);
  * Replaces conv_layer.cu:8-24 (K=147 im2col+SGEMM) + bn/scale/relu for layer conv1. */
 int dc_conv1_forward(const float* x, int n, int h, int w, const float* w147x64, const float* scale,
                      const float* shift, void* out, void* stream);
+/* Tensor-core stem: the same layer as dc_conv1_forward, computed as a 4x4 stride-1 convolution over the
+ * 2x2 space-to-depth image on the tcgen05 kernel.  workspace: device scratch of dc_conv1_tc_workspace_bytes()
+ * bytes; w_packed/scale/shift from dc_pack_conv1_tc_weight (host) uploaded by the caller
+ * (scale[c] = folded a[c] * rowscale[c]). */
+size_t dc_conv1_tc_workspace_bytes(int n, int h, int w);
+/* W[64][3][7][7] -> split fp16 [2][64][256], K = p*64 + q*16 + (py*2+px)*3 + ci (zero where the 4x4x16
+ * window has no 7x7 tap), rows power-of-two scaled like dc_pack_conv_weight. */
+int dc_pack_conv1_tc_weight(const float* w, uint16_t* packed, float* rowscale);
+int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packed, const float* scale,
+                        const float* shift, void* workspace, void* out, void* stream);
 /* MAX pool, pad 0, ceil-mode (PoolingLayer::Forward_gpu, pooling_layer.cu:10-47,158-180). */
 int dc_maxpool_forward(const void* x, int n, int h, int w, int c, int kernel, int stride, void* out, void* stream);
 int dc_pool_out_size(int size, int kernel, int stride);

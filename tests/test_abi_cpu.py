@@ -98,3 +98,38 @@ def test_conv1_pack_and_pool_size():
     from oracle import caffe_ref
     for size in (5, 6, 7, 128, 129, 344, 360, 640):
         assert L.dc_pool_out_size(size, 3, 2) == caffe_ref.pool_out_size(size, 3, 0, 2)
+
+
+def test_conv1_tc_weight_mapping_reproduces_7x7_stride2():
+    """dc_pack_conv1_tc_weight lays the 7x7/2 filter out as a 4x4 stride-1 filter over the 2x2
+    space-to-depth image (16 ch per pixel).  Emulate stem_s2d_kernel + that convolution in numpy and
+    compare with the oracle's 7x7/2 convolution (conv_layer.cpp:8-40)."""
+    from oracle import caffe_ref
+    L = libdc.lib()
+    rng = np.random.default_rng(5)
+    w = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
+    packed = np.zeros((2, 64, 256), np.uint16)
+    rs = np.zeros(64, np.float32)
+    libdc.check(L.dc_pack_conv1_tc_weight(dcutil.ptr(w), dcutil.ptr(packed), dcutil.ptr(rs)))
+    wk = (packed[0].view(np.float16).astype(np.float64) + packed[1].view(np.float16).astype(np.float64)) * rs[:, None]   # [64][256]
+    assert abs(np.abs(wk).sum() - np.abs(w.astype(np.float64)).sum()) < 1e-3          # every tap placed exactly once
+    for (h, wd) in ((12, 16), (11, 13)):
+        x = rng.standard_normal((1, 3, h, wd)).astype(np.float32)
+        h2, w2 = (h + 1) // 2, (wd + 1) // 2
+        s2d = np.zeros((h2, w2 + 3, 16))
+        for py in range(2):
+            for px in range(2):
+                for ci in range(3):
+                    sub = x[0, ci, py::2, px::2]
+                    s2d[:sub.shape[0], 2:2 + sub.shape[1], (py * 2 + px) * 3 + ci] = sub
+        out = np.zeros((64, h2, w2))
+        for oy in range(h2):
+            for ox in range(w2):
+                k = np.zeros(256)
+                for p in range(4):
+                    yy = oy + p - 2
+                    if 0 <= yy < h2:
+                        k[p * 64:(p + 1) * 64] = s2d[yy, ox:ox + 4, :].reshape(64)
+                out[:, oy, ox] = wk @ k
+        ref = caffe_ref.convolution(x, w, None, 2, 3, 1)[0]
+        assert out.shape == ref.shape and np.abs(out - ref).max() < 1e-4

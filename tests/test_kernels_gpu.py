@@ -147,6 +147,37 @@ def test_conv1_stem(_gpu):
         assert np.abs(got - ref).max() < 1e-4, np.abs(got - ref).max()
 
 
+def test_conv1_stem_tensor_core(_gpu):
+    """dc_conv1_tc_forward: space-to-depth + overlapping-window tensor map + tcgen05 conv, vs the oracle."""
+    L = libdc.lib()
+    rng = np.random.default_rng(14)
+    for (n, h, w) in ((1, 64, 64), (2, 75, 101), (1, 720, 1280)):
+        x = dcutil.synth.images(n, h, w, seed=3)
+        wt = (rng.standard_normal((64, 3, 7, 7)) * np.sqrt(2.0 / 147)).astype(np.float32)
+        a, b = _bn_params(rng, 64)
+        a = (a / 70).astype(np.float32)
+        packed = np.zeros((2, 64, 256), np.uint16)
+        rs = np.zeros(64, np.float32)
+        libdc.check(L.dc_pack_conv1_tc_weight(dcutil.ptr(wt), dcutil.ptr(packed), dcutil.ptr(rs)))
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+        ws = torch.empty(L.dc_conv1_tc_workspace_bytes(n, h, w), dtype=torch.uint8, device="cuda")
+        out = torch.full((2, n, ho, wo, 64), float("nan"), dtype=torch.float16, device="cuda")
+        dx, dw, da, db = _gpu.dev(x), _gpu.dev(packed), _gpu.dev(a * rs), _gpu.dev(b)
+        libdc.check(L.dc_conv1_tc_forward(dx.data_ptr(), n, h, w, dw.data_ptr(), da.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                          out.data_ptr(), _gpu.stream_ptr()))
+        torch.cuda.synchronize()
+        got = dcutil.np_join(out.cpu().numpy())
+        if h * w > 100000:      # full 720p: fp64 spot checks instead of the whole oracle conv
+            xp = np.pad(x[0], ((0, 0), (3, 3), (3, 3))).astype(np.float64)
+            for _ in range(200):
+                c, oy, ox = rng.integers(64), rng.integers(ho), rng.integers(wo)
+                ref = max((xp[:, 2 * oy:2 * oy + 7, 2 * ox:2 * ox + 7] * wt[c]).sum() * a[c] + b[c], 0)
+                assert abs(got[0, c, oy, ox] - ref) < 1e-4
+        else:
+            ref = np.maximum(caffe_ref.convolution(x, wt, None, 2, 3, 1) * a.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1), 0)
+            assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-4, np.abs(got - ref).max()
+
+
 def test_maxpool_bit_exact(_gpu):
     L = libdc.lib()
     rng = np.random.default_rng(11)
