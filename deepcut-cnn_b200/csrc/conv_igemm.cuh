@@ -45,7 +45,8 @@ struct ConvParams {
   int ntaps;
   int tap_dy[kMaxTaps];     // input row/col offset of each tap relative to the output pixel
   int tap_dx[kMaxTaps];
-  int TH, TW;               // tile rectangle, TH * TW == 128
+  int TH, TW;               // tile rectangle, TH * TW == 128 (TW a power of two)
+  int log2_tw;
   int tiles_x, tiles_y;     // per image
   int n_tiles_m;            // N * tiles_y * tiles_x
   int n_tiles_n;            // ceil(Cout / BN)
@@ -240,12 +241,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int t_ty = t_mt % p.tiles_y;
       const int t_img = t_mt / p.tiles_y;
       if (t_nt * BN + c0 >= p.Cout) return;
+      // rows (lane >> 2) + 8 i of the warp's 32-row sub-rectangle (TW is a power of two: shifts, no divides)
+      const int yy0 = t_ty * p.TH + ((q * 32) >> p.log2_tw), xx0 = t_tx * p.TW + ((q * 32) & (p.TW - 1));
+      const long long pix0 = (static_cast<long long>(t_img) * p.Ho + yy0) * p.Wo + xx0;
+      const __half* base = p.res + t_nt * BN + c0 + (lane & 3) * 8;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int rr = q * 32 + (lane >> 2) + 8 * i;
-        const int yy = t_ty * p.TH + rr / p.TW, xx = t_tx * p.TW + rr % p.TW;
-        if (yy < p.Ho && xx < p.Wo) {
-          const __half* src = p.res + ((static_cast<long long>(t_img) * p.Ho + yy) * p.Wo + xx) * p.Cout + t_nt * BN + c0 + (lane & 3) * 8;
+        const int rr = (lane >> 2) + 8 * i;
+        const int dy = rr >> p.log2_tw, dx = rr & (p.TW - 1);
+        if (yy0 + dy < p.Ho && xx0 + dx < p.Wo) {
+          const __half* src = base + (pix0 + dy * p.Wo + dx) * p.Cout;
           res_h[i] = __ldg(reinterpret_cast<const uint4*>(src));
           res_l[i] = __ldg(reinterpret_cast<const uint4*>(src + p.res_plane));
         }
@@ -306,7 +311,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // stores (hi and lo plane) that clip ragged tile edges.
         uint8_t* stg = staging_all + (warp - 2) * 4096;
         const int r0 = q * 32;
-        const int box_x = tx * p.TW + r0 % p.TW, box_y = ty * p.TH + r0 / p.TW;
+        const int box_x = tx * p.TW + (r0 & (p.TW - 1)), box_y = ty * p.TH + (r0 >> p.log2_tw);
         const int piece = lane & 3;
         const int own_sw = (lane >> 1) & 3;                // swizzle of this thread's own row (row index == lane)
 #pragma unroll 1
@@ -350,35 +355,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), sc[j], sh[j]);
           uint8_t* my_hi = stg + lane * 64;
           uint8_t* my_lo = my_hi + 2048;
+          constexpr uint16_t kOneH = 0x3C00, kMinusOneH = 0xBC00;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int slot = (g ^ own_sw) << 4;
             if (p.res != nullptr) {
               const uint4 h4 = *reinterpret_cast<const uint4*>(my_hi + slot);
               const uint4 l4 = *reinterpret_cast<const uint4*>(my_lo + slot);
-              const __half2* hh = reinterpret_cast<const __half2*>(&h4);
-              const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
-                v[g * 8 + e * 2 + 0] += fh.x + fl.x;
-                v[g * 8 + e * 2 + 1] += fh.y + fl.y;
+                uint16_t h0, h1, l0, l1;
+                unpack_h2(hw[e], h0, h1);
+                unpack_h2(lw[e], l0, l1);
+                // v += hi + lo, one FHFMA each (fp16 * 1 + fp32)
+                v[g * 8 + e * 2 + 0] = fma_hhf(l0, kOneH, fma_hhf(h0, kOneH, v[g * 8 + e * 2 + 0]));
+                v[g * 8 + e * 2 + 1] = fma_hhf(l1, kOneH, fma_hhf(h1, kOneH, v[g * 8 + e * 2 + 1]));
               }
             }
-            uint4 h4, l4;
-            __half2* hh = reinterpret_cast<__half2*>(&h4);
-            __half2* ll = reinterpret_cast<__half2*>(&l4);
+            uint32_t ho[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float a = v[g * 8 + e * 2], b = v[g * 8 + e * 2 + 1];
               if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              const __half2 h2 = __floats2half2_rn(a, b);
-              const float2 hf = __half22float2(h2);
-              hh[e] = h2;
-              ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+              ho[e] = pack_f2h2_rn(a, b);
+              uint16_t ha, hb;
+              unpack_h2(ho[e], ha, hb);
+              lo[e] = pack_f2h2_rn(fma_hhf(ha, kMinusOneH, a), fma_hhf(hb, kMinusOneH, b));   // x - hi, exact in fp32
             }
-            *reinterpret_cast<uint4*>(my_hi + slot) = h4;
-            *reinterpret_cast<uint4*>(my_lo + slot) = l4;
+            *reinterpret_cast<uint4*>(my_hi + slot) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            *reinterpret_cast<uint4*>(my_lo + slot) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
@@ -389,8 +395,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       } else {   // kOutF32Rows
-        const int oy = ty * p.TH + row / p.TW;
-        const int ox = tx * p.TW + row % p.TW;
+        const int oy = ty * p.TH + (row >> p.log2_tw);
+        const int ox = tx * p.TW + (row & (p.TW - 1));
         const bool valid = tile_ok && (oy < p.Ho) && (ox < p.Wo);
         const long long pix = (static_cast<long long>(img) * p.Ho + oy) * p.Wo + ox;
 #pragma unroll 1

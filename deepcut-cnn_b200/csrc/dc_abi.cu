@@ -450,6 +450,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
     const long long area = static_cast<long long>((out_w + tw - 1) / tw) * tw * ((out_h + th - 1) / th) * th;
     if (best < 0 || area < best) { best = area; p.TW = tw; p.TH = th; }
   }
+  for (p.log2_tw = 0; (1 << p.log2_tw) < p.TW; ++p.log2_tw) {}
   p.tiles_x = (out_w + p.TW - 1) / p.TW;
   p.tiles_y = (out_h + p.TH - 1) / p.TH;
   p.n_tiles_m = n * p.tiles_x * p.tiles_y;
@@ -504,6 +505,7 @@ int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packe
     const long long area = static_cast<long long>((w2 + tw - 1) / tw) * tw * ((h2 + th - 1) / th) * th;
     if (best < 0 || area < best) { best = area; p.TW = tw; p.TH = th; }
   }
+  for (p.log2_tw = 0; (1 << p.log2_tw) < p.TW; ++p.log2_tw) {}
   p.tiles_x = (w2 + p.TW - 1) / p.TW;
   p.tiles_y = (h2 + p.TH - 1) / p.TH;
   p.n_tiles_m = n * p.tiles_x * p.tiles_y;

@@ -227,6 +227,23 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Mixed-precision FMA (PTX ISA 8.6+, sm_100): d = a * b + c with fp16 a, b and fp32 c, d (SASS FHFMA).
+// Used to add a split-fp16 residual (x * 1 + acc) and to form the lo plane (hi * -1 + x) without
+// separate cvt instructions.
+__device__ __forceinline__ float fma_hhf(uint16_t a, uint16_t b, float c) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void unpack_h2(uint32_t x, uint16_t& lo, uint16_t& hi) {
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(x));
+}
+__device__ __forceinline__ uint32_t pack_f2h2_rn(float lo, float hi) {   // cvt.rn.f16x2.f32: {hi, lo} -> one register
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // fp32 -> (hi, lo) fp16 pair with hi + lo == x to ~2^-22 relative (round-to-nearest both)
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
