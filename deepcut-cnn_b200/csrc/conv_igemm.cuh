@@ -128,6 +128,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CG == 2) cluster_sync_all();             // peer barriers are initialised before any remote arrive
   else __syncthreads();
   tc_fence_after();
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the
+  // previous kernel; from here on we read what it wrote.
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {

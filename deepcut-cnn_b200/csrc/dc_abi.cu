@@ -150,29 +150,39 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, long long K, int bn
   return DC_OK;
 }
 
+bool use_pdl() {
+  static const bool on = [] { const char* e = getenv("DC_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int BN, int CG>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st) {
   const int units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   int grid = units * CG < g_num_sms ? units * CG : g_num_sms;
   if (CG == 2) grid &= ~1;
-  if (CG == 1) {
-    dc::conv_igemm_kernel<BN, 1><<<grid, dc::kConvThreads, dc::ConvCfg<BN, 1>::kSmemBytes, st>>>(ta, tb, to, p);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(dc::kConvThreads);
-    cfg.dynamicSmemBytes = dc::ConvCfg<BN, 2>::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, 2>, ta, tb, to, p));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(dc::kConvThreads);
+  cfg.dynamicSmemBytes = dc::ConvCfg<BN, CG>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (use_pdl()) {     // the kernel's prologue overlaps the previous kernel's tail (griddepcontrol.wait inside)
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if (CG == 2) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = 2;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG>, ta, tb, to, p));
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
