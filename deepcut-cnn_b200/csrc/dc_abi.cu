@@ -595,6 +595,16 @@ int dc_head_finish(const float* col, long long ldcol, int col_off, const float* 
   return DC_OK;
 }
 
+int dc_pose_from_maps(const float* prob, const float* loc, int n, int joints, int h, int w, float stride,
+                      float locref_scale, float scale, float* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!prob || !loc || !out || n <= 0 || joints <= 0 || h <= 0 || w <= 0 || scale == 0.f) return fail(DC_ERR_INVALID, "dc_pose_from_maps: bad arguments");
+  dc::pose_from_maps_kernel<<<n * joints, 256, 0, static_cast<cudaStream_t>(stream)>>>(prob, loc, joints, h, w, stride, locref_scale, scale, out);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
 int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream) {
   if (int rc = ensure_init()) return rc;
   if (!x || !out) return fail(DC_ERR_INVALID, "dc_nchw_to_split: null argument");

@@ -269,6 +269,50 @@ __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// Pose read-out on the device (the demo's _pose_from_mats, python/pose/estimate_pose.py:131-143):
+// per image and joint j, the arg-max of prob[n, j] (first maximum in row-major order, like np.argmax),
+// then  y = (my*stride + stride/2 + loc[n, 2j+1, my, mx]*s) / scale,  x likewise with loc[n, 2j].
+// out[n][5][J] = {x, y, confidence, loc[2j+1]*s/scale, loc[2j]*s/scale}  (the demo's row order).
+// One CTA per (n, joint); block-wide arg-max by warp shuffles, ties broken towards the lower index.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pose_from_maps_kernel(const float* __restrict__ prob, const float* __restrict__ loc,
+                                                             int J, int H, int W, float stride, float locref_scale,
+                                                             float scale, float* __restrict__ out) {
+  const int n = blockIdx.x / J, j = blockIdx.x % J;
+  const int plane = H * W;
+  const float* pm = prob + (static_cast<long long>(n) * J + j) * plane;
+  float best = -3.402823466e+38f;
+  int besti = 0x7fffffff;
+  for (int i = threadIdx.x; i < plane; i += blockDim.x) {
+    const float v = __ldg(pm + i);
+    if (v > best) { best = v; besti = i; }        // strictly greater: keeps the first maximum of this thread's stride
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = besti; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k)
+      if (sv[k] > best || (sv[k] == best && si[k] < besti)) { best = sv[k]; besti = si[k]; }
+    const int my = besti / W, mx = besti % W;
+    const float* lp = loc + (static_cast<long long>(n) * 2 * J + 2 * j) * plane + besti;
+    const float off_x = __ldg(lp) * locref_scale, off_y = __ldg(lp + plane) * locref_scale;
+    float* o = out + static_cast<long long>(n) * 5 * J + j;
+    o[0 * J] = (mx * stride + 0.5f * stride + off_x) / scale;
+    o[1 * J] = (my * stride + 0.5f * stride + off_y) / scale;
+    o[2 * J] = best;
+    o[3 * J] = off_y / scale;
+    o[4 * J] = off_x / scale;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Layout converters (blob materialisation / test harness): fp32 NCHW <-> split-fp16 NHWC.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ in, __half* __restrict__ out,

@@ -143,6 +143,11 @@ int dc_subsample_forward(const void* x, int n, int h, int w, int c, int stride, 
  * out: fp32 NCHW [n][cout][ho][wo]. */
 int dc_head_finish(const float* col, long long ldcol, int col_row0, const float* skip, long long ldskip, int skip_row0,
                    float* out, int n, int cout, int h, int w, int ho, int wo, int sigmoid, void* stream);
+/* Pose read-out of the demo on the device (python/pose/estimate_pose.py:131-143, _pose_from_mats):
+ * per image n and joint j: arg-max of prob[n][j] (first maximum, row-major), refined by loc[n][2j..2j+1] at
+ * that cell.  out: fp32 [n][5][joints] = {x, y, confidence, offset_y, offset_x} exactly as the demo lays them out. */
+int dc_pose_from_maps(const float* prob, const float* loc, int n, int joints, int h, int w, float stride,
+                      float locref_scale, float scale, float* out, void* stream);
 /* Blob materialisation: fp32 NCHW <-> split NHWC. */
 int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream);
 int dc_split_to_nchw(const void* x, int n, int c, int h, int w, float* out, void* stream);

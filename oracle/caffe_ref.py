@@ -210,6 +210,21 @@ def sigmoid(x):
     return (F32(1) / (F32(1) + np.exp(-x.astype(F32)))).astype(F32)
 
 
+def pose_from_mats(prob, loc, scale=1.0, stride=8.0, locref_scale=math.sqrt(53.0)):
+    """The demo's read-out, python/pose/estimate_pose.py:131-143 (_pose_from_mats) on the blob layouts of
+    :224-243 (_cnn_process_image): prob [14,H,W], loc [28,H,W] -> pose [5,14]."""
+    J = prob.shape[0]
+    offmat = loc.reshape(J, 2, loc.shape[1], loc.shape[2]).transpose(2, 3, 0, 1)   # [y][x][joint][2]
+    scoremat = prob.transpose(1, 2, 0)
+    pose = []
+    for j in range(J):
+        maxloc = np.unravel_index(np.argmax(scoremat[:, :, j]), scoremat[:, :, j].shape)
+        offset = np.array(offmat[maxloc][j])[::-1]
+        pos_f8 = np.array(maxloc).astype("float") * stride + 0.5 * stride + offset * locref_scale
+        pose.append(np.hstack((pos_f8[::-1] / scale, [scoremat[maxloc][j]], offset * locref_scale / scale)))
+    return np.array(pose).T
+
+
 # --------------------------------------------------------------------------
 # Net (net.cpp:40-284 Init, :565-581 ForwardFromTo)
 # --------------------------------------------------------------------------

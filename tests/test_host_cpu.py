@@ -141,3 +141,32 @@ def test_errors_are_exceptions_not_aborts(tmp_path):
     with pytest.raises(Exception):
         net.params["conv1"][0].reshape(1, 2, 3)
         net.copy_from("/nonexistent.caffemodel")
+
+
+def test_shim_covers_every_caffe_name_the_reference_demo_uses():
+    """python/pose/estimate_pose.py and pose_demo.py only touch a small pycaffe surface; every attribute they
+    use on the `caffe` module, on the Net and on a Blob must exist in the shim (checked by AST, here where the
+    reference is mounted; the Python-2 files themselves are not executed)."""
+    import ast
+    ref = "/root/reference/python/pose"
+    if not os.path.isdir(ref):
+        pytest.skip("reference not mounted on this box")
+    used_module, used_obj = set(), set()
+    for fn in ("estimate_pose.py", "pose_demo.py"):
+        tree = ast.parse(open(os.path.join(ref, fn)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id in ("caffe", "_caffe"):
+                used_module.add(node.attr)
+            if isinstance(node, ast.Attribute) and node.attr in ("blobs", "forward", "data", "reshape", "params", "inputs", "outputs"):
+                used_obj.add(node.attr)
+    assert used_module == {"Net", "TEST", "set_mode_gpu", "set_mode_cpu", "set_device"} or used_module <= {"Net", "TEST", "set_mode_gpu", "set_mode_cpu", "set_device"}
+    for name in used_module:
+        assert hasattr(caffe, name), name
+    assert {"blobs", "forward", "data", "reshape"} <= used_obj
+    path = dcutil.write_prototxt(__import__("tempfile").mkdtemp(), stages=(1, 1, 1, 1), height=64, width=64)
+    net = caffe.Net(path, caffe.TEST)
+    blob = net.blobs["data"]
+    blob.reshape(1, 3, 40, 48)                                    # estimate_pose.py:227
+    blob.data[0, ...] = np.ones((3, 40, 48), np.float32)          # :228
+    assert blob.data.shape == (1, 3, 40, 48) and float(blob.data.sum()) == 3 * 40 * 48
+    assert callable(net.forward) and "loc_pred" in net.blobs and "prob" in net.blobs      # :229-232

@@ -273,6 +273,26 @@ def test_deconv_head_pipeline(_gpu):
             off += co
 
 
+def test_pose_from_maps_matches_demo_readout(_gpu):
+    L = libdc.lib()
+    rng = np.random.default_rng(15)
+    for (n, h, w, scale) in ((2, 90, 160, 1.0), (1, 33, 47, 0.5), (3, 8, 8, 1.5)):
+        prob = rng.random((n, 14, h, w)).astype(np.float32)
+        prob[0, 3] = 0.25                      # a constant map: arg-max must be index 0 like np.argmax
+        prob[0, 5, h // 2, w // 3] = prob[0, 5, h - 1, w - 1] = 2.0       # tie: the first one wins
+        loc = rng.standard_normal((n, 28, h, w)).astype(np.float32)
+        out = torch.zeros((n, 5, 14), dtype=torch.float32, device="cuda")
+        dp, dl = _gpu.dev(prob), _gpu.dev(loc)
+        libdc.check(L.dc_pose_from_maps(dp.data_ptr(), dl.data_ptr(), n, 14, h, w, 8.0, float(np.sqrt(53.0)), scale, out.data_ptr(),
+                                        _gpu.stream_ptr()))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for i in range(n):
+            ref = caffe_ref.pose_from_mats(prob[i], loc[i], scale=scale)
+            assert np.abs(got[i] - ref).max() < 1e-3, (i, np.abs(got[i] - ref).max())
+            assert np.array_equal(got[i][2], ref[2].astype(np.float32))      # confidences are exact copies
+
+
 def test_launch_counter_moves(_gpu):
     before = libdc.lib().dc_launch_count()
     test_subsample_and_layout_roundtrip(_gpu)
