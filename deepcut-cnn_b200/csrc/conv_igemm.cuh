@@ -34,7 +34,8 @@ namespace dc {
 constexpr int kBM = 128;        // output pixels per tile (TMEM lanes)
 constexpr int kBK = 64;         // fp16 channels per K-chunk = one 128-byte swizzle row
 constexpr int kMaxTaps = 9;
-constexpr int kConvThreads = 320;    // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kConvThreads = 320;    // TMA warp, MMA warp, 8 epilogue warps (EW = 8)
+constexpr int conv_threads(int ew) { return 64 + 32 * ew; }
 
 enum OutMode : int { kOutSplitNHWC = 0, kOutF32Rows = 1, kOutF32RowsT = 2 };
 
@@ -66,24 +67,28 @@ struct ConvParams {
 // computes two vertically adjacent 128-pixel tiles against the same BN channels; each CTA stages its
 // own 128 A rows but only BN/2 rows of B, so the bytes every SM pulls from L2 per MMA drop by 25 %
 // (64 KB -> 48 KB per K-chunk) and a fourth pipeline stage fits in shared memory.
-template <int BN, int CG = 1>
+// EW = epilogue warps: 8 (two per TMEM lane quarter, two 32-channel chunks each per tile; r/rx/prefetch in
+// registers) or 16 ("lean" epilogue for the epilogue-bound 1x1 expand convs: one chunk per warp, 16-column
+// TMEM loads, residual brought in by cp.async, ~100 registers/thread; costs one pipeline stage of smem).
+template <int BN, int CG = 1, int EW = 8>
 struct ConvCfg {
   static constexpr int kABytes = kBM * kBK * 2;          // one plane of A per stage
   static constexpr int kBRows = BN / CG;                 // B rows resident in THIS CTA
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static_assert(BN == 64 || BN == 128, "4 accumulators of BN columns must fit 512 TMEM columns");
-  static constexpr int kStages = CG == 2 ? 4 : (BN >= 128 ? 3 : 4);
+  static_assert(EW == 8 || (EW == 16 && BN == 128), "the 16-warp epilogue owns one 32-channel chunk per warp: BN = 128");
+  static constexpr int kStages = (CG == 2 ? 4 : (BN >= 128 ? 3 : 4)) - (EW == 16 ? 1 : 0);
   static constexpr int kTmemCols = 4 * BN;                         // 2 x (main, cross)
-  static constexpr int kStagingBytes = 8 * 4096;         // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo}
+  static constexpr int kStagingBytes = EW * 4096;        // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo}
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int CG>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN, int CG, int EW>
+__global__ void __launch_bounds__(conv_threads(EW), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
-  using Cfg = ConvCfg<BN, CG>;
+  using Cfg = ConvCfg<BN, CG, EW>;
   const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   // work units: (m-tile group of CG tiles, n-tile); unit u -> n-tile u % n_tiles_n, m-tile CG * (u / n_tiles_n) + rank
   const int unit_first = CG == 2 ? (blockIdx.x >> 1) : blockIdx.x;
@@ -116,7 +121,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8 * CG);      // every epilogue warp of every CTA of the group
+      mbar_init(&tempty_bar[a], EW * CG);     // every epilogue warp of every CTA of the group
     }
     fence_mbar_init();
   }
@@ -225,6 +230,143 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (EW == 16) {
+    // ------------------------------------------------------------ lean epilogue (warps 2..17), split-NHWC only
+    // One 32-pixel x 32-channel chunk per warp per tile.  The residual chunk is copied global -> staging by
+    // cp.async as soon as the previous tile's TMA stores have drained the staging tile, i.e. while the
+    // next accumulator is still being computed; accumulators are read 16 columns at a time.
+    const int q = warp & 3;
+    const int c0 = ((warp - 2) >> 2) * 32;
+    uint8_t* stg = staging_all + (warp - 2) * 4096;
+    const int piece = lane & 3;
+    const int own_sw = (lane >> 1) & 3;
+    const bool has_res = p.res != nullptr;
+    auto issue_residual = [&](int u) {
+      if (u >= total_units) return;
+      const int t_nt = u % p.n_tiles_n;
+      int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
+      if (t_mt >= p.n_tiles_m || t_nt * BN + c0 >= p.Cout) return;
+      const int t_tx = t_mt % p.tiles_x;
+      t_mt /= p.tiles_x;
+      const int t_ty = t_mt % p.tiles_y;
+      const int t_img = t_mt / p.tiles_y;
+      const int yy0 = t_ty * p.TH + ((q * 32) >> p.log2_tw), xx0 = t_tx * p.TW + ((q * 32) & (p.TW - 1));
+      const long long pix0 = (static_cast<long long>(t_img) * p.Ho + yy0) * p.Wo + xx0;
+      const __half* base = p.res + t_nt * BN + c0 + piece * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        const int dy = rr >> p.log2_tw, dx = rr & (p.TW - 1);
+        if (yy0 + dy < p.Ho && xx0 + dx < p.Wo) {      // rows outside the image are clipped by the TMA store: leave garbage
+          const __half* src = base + (pix0 + dy * p.Wo + dx) * p.Cout;
+          uint8_t* dst = stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4);
+          cp_async_16(dst, src);
+          cp_async_16(dst + 2048, src + p.res_plane);
+        }
+      }
+      cp_async_commit();
+    };
+    if (has_res) issue_residual(unit_first);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+      const int nt = unit % p.n_tiles_n;
+      int mt = (unit / p.n_tiles_n) * CG + cta_rank;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int n0 = nt * BN;
+      const bool chunk_ok = n0 + c0 < p.Cout;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 2 * BN) + c0;
+      uint8_t* my_hi = stg + lane * 64;
+      uint8_t* my_lo = my_hi + 2048;
+      constexpr uint16_t kOneH = 0x3C00, kMinusOneH = 0xBC00;
+      auto process16 = [&](const uint32_t (&a)[16], const uint32_t (&b)[16], int g0) {
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          const int g = g0 + gg;
+          const int slot = (g ^ own_sw) << 4;
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0) + 2 * g);
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0) + 2 * g + 1);
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c0) + 2 * g);
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c0) + 2 * g + 1);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[e] = fmaf(__uint_as_float(a[gg * 8 + e]) + __uint_as_float(b[gg * 8 + e]), sc[e], sh[e]);
+          if (has_res) {
+            const uint4 h4 = *reinterpret_cast<const uint4*>(my_hi + slot);
+            const uint4 l4 = *reinterpret_cast<const uint4*>(my_lo + slot);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint16_t h0, h1, l0, l1;
+              unpack_h2(hw[e], h0, h1);
+              unpack_h2(lw[e], l0, l1);
+              v[e * 2 + 0] = fma_hhf(l0, kOneH, fma_hhf(h0, kOneH, v[e * 2 + 0]));
+              v[e * 2 + 1] = fma_hhf(l1, kOneH, fma_hhf(h1, kOneH, v[e * 2 + 1]));
+            }
+          }
+          uint32_t ho[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0 = v[e * 2], x1 = v[e * 2 + 1];
+            if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            ho[e] = pack_f2h2_rn(x0, x1);
+            uint16_t ha, hb;
+            unpack_h2(ho[e], ha, hb);
+            lo[e] = pack_f2h2_rn(fma_hhf(ha, kMinusOneH, x0), fma_hhf(hb, kMinusOneH, x1));
+          }
+          *reinterpret_cast<uint4*>(my_hi + slot) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+          *reinterpret_cast<uint4*>(my_lo + slot) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      };
+      if (chunk_ok) {
+        uint32_t a[16], b[16];
+        tmem_ld_32x16(taddr, a);
+        tmem_ld_32x16(taddr + BN, b);
+        if (has_res) { cp_async_wait_all(); __syncwarp(); }      // this tile's residual chunk is in the staging tile
+        tmem_ld_wait();
+        process16(a, b, 0);
+        tmem_ld_32x16(taddr + 16, a);
+        tmem_ld_32x16(taddr + BN + 16, b);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                          // the accumulator is free for tile i+2
+          if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+        process16(a, b, 2);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int r0 = q * 32;
+          const int box_x = tx * p.TW + (r0 & (p.TW - 1)), box_y = ty * p.TH + (r0 >> p.log2_tw);
+          tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
+          tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
+          tma_store_commit();
+          tma_store_wait_read();                                  // staging tile drained: safe to refill
+        }
+        __syncwarp();
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+      }
+      if (has_res) issue_residual(unit + unit_stride);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     // Two warps per TMEM lane quarter; they split the tile's 32-column chunks between them.

@@ -155,7 +155,7 @@ bool use_pdl() {
   return on;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int EW = 8>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st) {
   const int units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   int grid = units * CG < g_num_sms ? units * CG : g_num_sms;
@@ -163,8 +163,8 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(dc::kConvThreads);
-  cfg.dynamicSmemBytes = dc::ConvCfg<BN, CG>::kSmemBytes;
+  cfg.blockDim = dim3(dc::conv_threads(EW));
+  cfg.dynamicSmemBytes = dc::ConvCfg<BN, CG, EW>::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;
@@ -182,7 +182,7 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG>, ta, tb, to, p));
+  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG, EW>, ta, tb, to, p));
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
@@ -237,10 +237,11 @@ int dc_init(int device) {
     if (!fn || q != cudaDriverEntryPointSuccess) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 1>::kSmemBytes));
-  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 1>::kSmemBytes));
-  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2>::kSmemBytes));
-  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 2>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 1, 8>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 1, 8>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2, 8>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 2, 8>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2, 16>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::kC1SmemFloats * 4));
   g_inited = true;
   return DC_OK;
@@ -487,6 +488,10 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair_mode ? bn / 2 : bn)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool pair = use_2cta() && !p.swap_ab && g_num_sms >= 2;
+  // epilogue-bound layers (short K, wide output: the 1x1 expand convs) get the 16-warp lean epilogue
+  static const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
+  const bool lean = lean_on && pair && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.ntaps * p.Cin <= 512 && a->cout >= 256;
+  if (lean) return launch_conv<128, 2, 16>(ta, tb, to, p, st);
   if (bn == 128) return pair ? launch_conv<128, 2>(ta, tb, to, p, st) : launch_conv<128, 1>(ta, tb, to, p, st);
   return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
 }
