@@ -490,7 +490,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   const bool pair = use_2cta() && !p.swap_ab && g_num_sms >= 2;
   // epilogue-bound layers (short K, wide output: the 1x1 expand convs) get the 16-warp lean epilogue
   static const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
-  const bool lean = lean_on && pair && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.ntaps * p.Cin <= 512 && a->cout >= 256;
+  const bool lean = lean_on && pair && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res != nullptr && p.ntaps * p.Cin <= 512 && a->cout >= 256;
   if (lean) return launch_conv<128, 2, 16>(ta, tb, to, p, st);
   if (bn == 128) return pair ? launch_conv<128, 2>(ta, tb, to, p, st) : launch_conv<128, 1>(ta, tb, to, p, st);
   return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
