@@ -14,6 +14,8 @@
 // A topology the matcher does not recognise makes Build() return NULL with a diagnostic and the Net
 // falls back to per-layer Forward_gpu.
 #pragma once
+#include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -21,15 +23,32 @@
 
 namespace caffe {
 
+// Device copies of the transformed weights (packed split-fp16 matrices, folded scale/shift), shared by
+// successive plans of one Net: a reshape re-plans shapes and the arena but does not re-pack 263 MB of
+// weights.  Dropped when a parameter blob is written on the host (SyncedMemory::host_write_epoch).
+class PlanWeightCache {
+ public:
+  struct Entry { void* w = nullptr; float* scale = nullptr; float* shift = nullptr; };
+  ~PlanWeightCache();
+  bool Stale() const;
+  void Snapshot(Net<float>& net);
+  std::map<std::string, Entry> entries;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+
+ private:
+  std::vector<std::pair<SyncedMemory*, unsigned long long> > epochs_;
+};
+
 class FusedPlan {
  public:
-  static FusedPlan* Build(Net<float>& net, bool materialize, std::string* why_not);
+  static FusedPlan* Build(Net<float>& net, bool materialize, std::string* why_not, std::shared_ptr<PlanWeightCache>* cache);
   ~FusedPlan();
   void Run();
   // true when a parameter blob was written on the host since the weights were packed
   bool WeightsStale() const;
   size_t arena_bytes() const { return arena_bytes_; }
-  size_t weight_bytes() const { return weight_bytes_; }
+  size_t weight_bytes() const { return weights_ ? weights_->bytes : 0; }
   int num_steps() const { return static_cast<int>(steps_.size()); }
   std::string Describe() const;
   // Per-step device timing: when enabled Run() brackets every step with CUDA events on the forward
@@ -53,13 +72,16 @@ class FusedPlan {
   std::vector<Step*> steps_;
   void* arena_ = nullptr;
   size_t arena_bytes_ = 0;
-  size_t weight_bytes_ = 0;
-  std::vector<void*> weight_allocs_;
+  std::shared_ptr<PlanWeightCache> weights_;
   std::vector<int> split_layers_;     // Split layer ids to alias after a materialised run
   bool materialize_ = false;
   bool step_timing_ = false;
+  // CUDA graph of the step sequence, valid while the blob device pointers it baked in are unchanged
+  void* graph_ = nullptr;
+  std::vector<const void*> graph_ptrs_;
+  bool graph_failed_ = false;
+  void IssueSteps(const std::vector<const void*>& blob_ptrs, void* stream);
   std::vector<void*> events_;
-  std::vector<std::pair<SyncedMemory*, unsigned long long> > weight_epochs_;
 };
 
 }  // namespace caffe

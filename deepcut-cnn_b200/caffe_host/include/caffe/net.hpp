@@ -12,6 +12,7 @@
 namespace caffe {
 
 class FusedPlan;
+class PlanWeightCache;
 
 template <typename Dtype>
 class Net {
@@ -115,6 +116,7 @@ class Net {
   string fusion_diag_;
   long long last_launches_ = 0;
   FusedPlan* plan_ = nullptr;
+  shared_ptr<PlanWeightCache> plan_weights_;   // survives re-planning on reshape
   vector<vector<int> > plan_input_shapes_;
 
   DISABLE_COPY_AND_ASSIGN(Net);

@@ -57,8 +57,8 @@ struct FusedPlan::Step {
 FusedPlan::~FusedPlan() {
   for (Tensor* t : tensors_) delete t;
   for (Step* s : steps_) delete s;
-  for (void* p : weight_allocs_) dc_free(p);
   for (void* e : events_) dc_event_destroy(e);
+  if (graph_) dc_graph_destroy(graph_);
   if (arena_) dc_free(arena_);
 }
 
@@ -389,8 +389,26 @@ size_t AlignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-FusedPlan* FusedPlan::Build(Net<float>& net, bool materialize, std::string* why_not) {
+PlanWeightCache::~PlanWeightCache() {
+  for (void* p : allocs) dc_free(p);
+}
+bool PlanWeightCache::Stale() const {
+  for (const auto& we : epochs_)
+    if (we.first->host_write_epoch() != we.second) return true;
+  return false;
+}
+void PlanWeightCache::Snapshot(Net<float>& net) {
+  epochs_.clear();
+  for (const auto& layer : net.layers())
+    for (const auto& blob : layer->blobs()) {
+      blob->cpu_data();     // make sure the SyncedMemory exists and is host-readable
+      epochs_.push_back(std::make_pair(blob->data().get(), blob->data()->host_write_epoch()));
+    }
+}
+
+FusedPlan* FusedPlan::Build(Net<float>& net, bool materialize, std::string* why_not, std::shared_ptr<PlanWeightCache>* cache) {
   FusedPlan* plan = new FusedPlan();
+  if (cache && *cache && !(*cache)->Stale()) plan->weights_ = *cache;
   plan->net_ = &net;
   plan->materialize_ = materialize;
   std::string why;
@@ -402,6 +420,7 @@ FusedPlan* FusedPlan::Build(Net<float>& net, bool materialize, std::string* why_
   if (why_not) why_not->clear();
   plan->PlanMemory();
   plan->UploadWeights(net);
+  if (cache) *cache = plan->weights_;
   return plan;
 }
 
@@ -503,24 +522,39 @@ void FusedPlan::PlanMemory() {
     if (t->bytes) t->ptr = static_cast<char*>(arena_) + t->offset;
 }
 
-bool FusedPlan::WeightsStale() const {
-  for (const auto& we : weight_epochs_)
-    if (we.first->host_write_epoch() != we.second) return true;
-  return false;
-}
+bool FusedPlan::WeightsStale() const { return !weights_ || weights_->Stale(); }
 
 void FusedPlan::UploadWeights(Net<float>& net) {
   void* stream = Caffe::stream();
-  for (const auto& layer : net.layers())
-    for (const auto& blob : layer->blobs()) {
-      blob->cpu_data();     // make sure the SyncedMemory exists and is host-readable
-      weight_epochs_.push_back(std::make_pair(blob->data().get(), blob->data()->host_write_epoch()));
+  const bool reuse = static_cast<bool>(weights_);
+  if (!reuse) {
+    weights_.reset(new PlanWeightCache());
+    weights_->Snapshot(net);
+  }
+  PlanWeightCache& wc = *weights_;
+  // steps are keyed by type + name: the same layers fuse the same way whatever the input shape
+  auto key_of = [](const Step* st) { return std::to_string(static_cast<int>(st->type)) + (st->stem_tc ? "t:" : ":") + st->name; };
+  if (reuse) {
+    bool all = true;
+    for (Step* st : steps_)
+      if ((st->type == Step::kConv1 || st->type == Step::kConvBN || st->type == Step::kHeadGemm) && !wc.entries.count(key_of(st))) all = false;
+    if (all) {
+      for (Step* st : steps_) {
+        auto it = wc.entries.find(key_of(st));
+        if (it == wc.entries.end()) continue;
+        st->w_dev = it->second.w; st->scale_dev = it->second.scale; st->shift_dev = it->second.shift;
+      }
+      return;
     }
+    weights_.reset(new PlanWeightCache());      // topology changed under the same weights: start over
+    weights_->Snapshot(net);
+    return UploadWeights(net);
+  }
   auto upload = [&](const void* host, size_t bytes) {
     void* d = nullptr;
     DC_CHECK(dc_malloc(&d, bytes));
-    weight_allocs_.push_back(d);
-    weight_bytes_ += bytes;
+    wc.allocs.push_back(d);
+    wc.bytes += bytes;
     DC_CHECK(dc_memcpy_async(d, host, bytes, DC_H2D, stream));
     DC_CHECK(dc_stream_sync(stream));      // the host staging buffer is reused right after
     return d;
@@ -624,13 +658,49 @@ void FusedPlan::UploadWeights(Net<float>& net) {
       }
       st->shift_dev = static_cast<float*>(upload(shift.data(), rows * 4));
     }
+    if (st->w_dev) {
+      PlanWeightCache::Entry e;
+      e.w = st->w_dev; e.scale = st->scale_dev; e.shift = st->shift_dev;
+      wc.entries[key_of(st)] = e;
+    }
   }
 }
 
+// Blob device pointers the steps read/write, resolved OUTSIDE any graph capture (gpu_data() may upload the
+// input; overwrite_gpu_data() may allocate): one entry per step, nullptr when the step touches no blob.
 void FusedPlan::Run() {
   Net<float>& net = *net_;
   void* stream = Caffe::stream();
-  auto blob_in = [&](Tensor* t) { return net.blobs()[t->blob]->gpu_data(); };
+  std::vector<const void*> ptrs(steps_.size(), nullptr);
+  for (size_t i = 0; i < steps_.size(); ++i) {
+    const Step* st = steps_[i];
+    if (st->type == Step::kConv1) ptrs[i] = net.blobs()[st->in->blob]->gpu_data();
+    else if (st->type == Step::kHeadFinish || st->type == Step::kToBlob) ptrs[i] = net.blobs()[st->out_blob]->overwrite_gpu_data();
+  }
+  static const bool graphs_on = [] { const char* e = getenv("DC_CUDA_GRAPH"); return !(e && e[0] == '0'); }();
+  if (graphs_on && !step_timing_ && !graph_failed_) {
+    if (graph_ != nullptr && ptrs != graph_ptrs_) { dc_graph_destroy(graph_); graph_ = nullptr; }
+    if (graph_ == nullptr) {
+      if (dc_graph_begin(stream) == 0) {
+        IssueSteps(ptrs, stream);
+        if (dc_graph_end(stream, &graph_) != 0) { graph_ = nullptr; graph_failed_ = true; LOG(WARNING) << "CUDA graph capture failed (" << DcLastError() << "); launching step by step"; }
+        else graph_ptrs_ = ptrs;
+      } else {
+        graph_failed_ = true;
+      }
+    }
+    if (graph_ != nullptr) {
+      DC_CHECK(dc_graph_launch(graph_, stream));
+      for (int l : split_layers_) net.layers()[l]->Forward(net.bottom_vecs()[l], net.top_vecs()[l]);
+      return;
+    }
+  }
+  IssueSteps(ptrs, stream);
+  for (int l : split_layers_) net.layers()[l]->Forward(net.bottom_vecs()[l], net.top_vecs()[l]);
+}
+
+void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stream) {
+  Net<float>& net = *net_;
   if (step_timing_ && events_.size() != steps_.size() + 1) {
     for (void* e : events_) dc_event_destroy(e);
     events_.assign(steps_.size() + 1, nullptr);
@@ -639,15 +709,16 @@ void FusedPlan::Run() {
   size_t step_index = 0;
   for (Step* st : steps_) {
     if (step_timing_) DC_CHECK(dc_event_record(events_[step_index], stream));
+    const void* bp = blob_ptrs[step_index];
     ++step_index;
     switch (st->type) {
       case Step::kConv1: {
+        const float* x = static_cast<const float*>(bp);
         if (st->stem_tc)
-          DC_CHECK(dc_conv1_tc_forward(blob_in(st->in), st->in->n, st->in->h, st->in->w, st->w_dev, st->scale_dev, st->shift_dev,
-                                       st->ws->ptr, st->out->ptr, stream));
+          DC_CHECK(dc_conv1_tc_forward(x, st->in->n, st->in->h, st->in->w, st->w_dev, st->scale_dev, st->shift_dev, st->ws->ptr, st->out->ptr, stream));
         else
-          DC_CHECK(dc_conv1_forward(blob_in(st->in), st->in->n, st->in->h, st->in->w, static_cast<const float*>(st->w_dev), st->scale_dev,
-                                    st->shift_dev, st->out->ptr, stream));
+          DC_CHECK(dc_conv1_forward(x, st->in->n, st->in->h, st->in->w, static_cast<const float*>(st->w_dev), st->scale_dev, st->shift_dev,
+                                    st->out->ptr, stream));
         break;
       }
       case Step::kConvBN:
@@ -674,19 +745,16 @@ void FusedPlan::Run() {
       case Step::kHeadFinish: {
         Blob<float>* ob = net.blobs()[st->out_blob].get();
         DC_CHECK(dc_head_finish(static_cast<const float*>(st->col->ptr), st->col->ld, st->col_off, static_cast<const float*>(st->in2->ptr),
-                                st->in2->ld, st->skip_off, ob->overwrite_gpu_data(), st->in->n, st->cout, st->in->h, st->in->w, ob->height(),
-                                ob->width(), st->sigmoid, stream));
+                                st->in2->ld, st->skip_off, static_cast<float*>(const_cast<void*>(bp)), st->in->n, st->cout, st->in->h, st->in->w,
+                                ob->height(), ob->width(), st->sigmoid, stream));
         break;
       }
-      case Step::kToBlob: {
-        Blob<float>* ob = net.blobs()[st->out_blob].get();
-        DC_CHECK(dc_split_to_nchw(st->in->ptr, st->in->n, st->in->c, st->in->h, st->in->w, ob->overwrite_gpu_data(), stream));
+      case Step::kToBlob:
+        DC_CHECK(dc_split_to_nchw(st->in->ptr, st->in->n, st->in->c, st->in->h, st->in->w, static_cast<float*>(const_cast<void*>(bp)), stream));
         break;
-      }
     }
   }
   if (step_timing_) DC_CHECK(dc_event_record(events_[step_index], stream));
-  for (int l : split_layers_) net.layers()[l]->Forward(net.bottom_vecs()[l], net.top_vecs()[l]);
 }
 
 std::vector<FusedPlan::StepInfo> FusedPlan::LastStepInfo() {
@@ -745,7 +813,7 @@ std::vector<FusedPlan::StepInfo> FusedPlan::LastStepInfo() {
 std::string FusedPlan::Describe() const {
   std::ostringstream s;
   static const char* kNames[] = {"Conv1", "ConvBN", "Subsample", "MaxPool", "HeadGemm", "HeadFinish", "ToBlob"};
-  s << steps_.size() << " steps, arena " << (arena_bytes_ >> 20) << " MiB, weights " << (weight_bytes_ >> 20) << " MiB\n";
+  s << steps_.size() << " steps, arena " << (arena_bytes_ >> 20) << " MiB, weights " << (weight_bytes() >> 20) << " MiB\n";
   for (const Step* st : steps_) {
     s << "  " << kNames[st->type] << " " << st->name;
     if (st->in) s << " in=" << st->in->n << "x" << st->in->c << "x" << st->in->h << "x" << st->in->w;

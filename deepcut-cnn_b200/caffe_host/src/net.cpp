@@ -199,7 +199,7 @@ const vector<Blob<Dtype>*>& Net<Dtype>::ForwardPrefilled(Dtype* loss) {
       delete plan_;
       plan_ = nullptr;
       Reshape();                       // propagate input shapes like Layer::Forward's per-call Reshape
-      plan_ = FusedPlan::Build(*reinterpret_cast<Net<float>*>(this), materialize_, &fusion_diag_);
+      plan_ = FusedPlan::Build(*reinterpret_cast<Net<float>*>(this), materialize_, &fusion_diag_, &plan_weights_);
       plan_input_shapes_ = shapes;
       if (plan_ == nullptr) LOG(WARNING) << "fused plan unavailable (" << fusion_diag_ << "); running layer by layer";
     }
@@ -238,8 +238,8 @@ void Net<Dtype>::Reshape() {
 }
 
 template <typename Dtype> void Net<Dtype>::set_fusion(bool on) { fusion_ = on; }
-template <typename Dtype> void Net<Dtype>::materialize_intermediates(bool on) { if (on != materialize_) { materialize_ = on; InvalidatePlan(); } }
-template <typename Dtype> void Net<Dtype>::InvalidatePlan() { delete plan_; plan_ = nullptr; }
+template <typename Dtype> void Net<Dtype>::materialize_intermediates(bool on) { if (on != materialize_) { materialize_ = on; delete plan_; plan_ = nullptr; } }
+template <typename Dtype> void Net<Dtype>::InvalidatePlan() { delete plan_; plan_ = nullptr; plan_weights_.reset(); }
 
 // --------------------------------------------------------------------------------------- weights
 template <typename Dtype>

@@ -314,6 +314,46 @@ int dc_event_elapsed_ms(void* start, void* stop, float* ms) {
   return DC_OK;
 }
 
+// ------------------------------------------------------------------ CUDA graphs
+namespace {
+struct GraphExec { cudaGraphExec_t exec; long long launches; };
+thread_local long long g_capture_base = -1;
+}  // namespace
+
+int dc_graph_begin(void* stream) {
+  if (int rc = ensure_init()) return rc;
+  DC_CUDA(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal));
+  g_capture_base = g_launches.load();
+  return DC_OK;
+}
+int dc_graph_end(void* stream, void** graph_exec) {
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &graph);
+  const long long captured = g_launches.load() - g_capture_base;
+  g_launches -= captured;       // captured launches have not run yet; dc_graph_launch counts them per replay
+  g_capture_base = -1;
+  if (e != cudaSuccess || graph == nullptr) { cudaGetLastError(); return fail(DC_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e)); }
+  GraphExec* g = new GraphExec();
+  g->launches = captured;
+  e = cudaGraphInstantiate(&g->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { delete g; cudaGetLastError(); return fail(DC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  *graph_exec = g;
+  return DC_OK;
+}
+int dc_graph_launch(void* graph_exec, void* stream) {
+  GraphExec* g = static_cast<GraphExec*>(graph_exec);
+  if (!g) return fail(DC_ERR_INVALID, "dc_graph_launch: null graph");
+  DC_CUDA(cudaGraphLaunch(g->exec, static_cast<cudaStream_t>(stream)));
+  g_launches += g->launches;
+  return DC_OK;
+}
+int dc_graph_destroy(void* graph_exec) {
+  GraphExec* g = static_cast<GraphExec*>(graph_exec);
+  if (g) { cudaGraphExecDestroy(g->exec); delete g; }
+  return DC_OK;
+}
+
 // ------------------------------------------------------------------ host-side transforms
 int dc_fold_bn_scale(const float* mean_sum, const float* var_sum, float factor, float eps, const float* gamma,
                      const float* beta, int channels, float* a_out, float* b_out) {

@@ -66,6 +66,14 @@ int dc_event_destroy(void* event);
 int dc_event_record(void* event, void* stream);
 int dc_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
 
+/* CUDA-graph capture of a launch sequence issued through this ABI on `stream` (per input shape: the fused
+ * plan replays ~164 launches, incl. their cluster / programmatic-dependent-launch attributes, from one
+ * cudaGraphLaunch instead of re-encoding tensor maps and re-launching every kernel). */
+int dc_graph_begin(void* stream);
+int dc_graph_end(void* stream, void** graph_exec);      /* ends capture and instantiates */
+int dc_graph_launch(void* graph_exec, void* stream);
+int dc_graph_destroy(void* graph_exec);
+
 /* ---- load-time weight transforms (host side, no GPU needed) ------------------------- */
 /* y = (x - mean*sf) / sqrt(var*sf + eps) * gamma + beta  ==  a*x + b with sf = (factor==0 ? 0 : 1/factor)
  * BatchNormLayer inference branch (src/caffe/layers/batch_norm_layer.cpp:86-93,137-149) folded with
