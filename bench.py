@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--model", default="152", choices=["152", "101"])
+    ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3"],
+                    help="BASELINE.json configs: cfg1 = batch 1 3x512x512, cfg2 = batch 16 3x720x1280 (default), cfg3 = batch 16/GPU 3x512x512")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--step-report", default=None, help="write the per-step roofline table to this path")
     return ap.parse_args()
@@ -142,6 +144,10 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------ B200 arm
 def main():
     args = parse_args()
+    if args.workload == "cfg1":
+        args.batch, args.height, args.width = 1, 512, 512
+    elif args.workload == "cfg3":
+        args.batch, args.height, args.width = 16, 512, 512
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
