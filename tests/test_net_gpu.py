@@ -116,6 +116,42 @@ def test_host_weight_write_invalidates_packed_cache(tmp_path):
         assert np.array_equal(b[k], c[k]), k
 
 
+def test_batch_independence_and_determinism(tmp_path):
+    """Images of a batch are independent (stored BN statistics, no cross-image reduction: SURVEY 8e), which is what
+    makes per-image sharding across GPUs exact: forward([a, b, c]) == [forward(a), forward(b), forward(c)] bitwise,
+    and repeated forwards are bitwise identical (no atomics / no run-to-run accumulation order changes)."""
+    path, weights = netutil.build(tmp_path, (1, 2, 2, 1), 96, 80)
+    net = netutil.product_net(path, weights)
+    x = dcutil.synth.images(3, 96, 80, seed=5)
+    full = netutil.product_forward(net, x)
+    again = netutil.product_forward(net, x)
+    for k in full:
+        assert np.array_equal(full[k], again[k]), k
+    for i in range(3):
+        one = netutil.product_forward(net, x[i:i + 1])
+        for k in full:
+            assert np.array_equal(one[k][0], full[k][i]), (k, i)
+
+
+def test_full_size_tile_grid_properties(tmp_path):
+    """BASELINE-size geometry (one 720p image: 90x160 output cells, ragged 45x80 res4/res5 maps) through the whole
+    fused net: outputs finite, prob in (0, 1), and the top-left 256x256 crop's outputs agree with the full image's
+    on the cells whose receptive field (< 16 cells of context here) lies inside the crop -- checks every kernel's edge
+    handling at the real sizes without running the CPU oracle on 555 GFLOP."""
+    path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
+    net = netutil.product_net(path, weights)
+    x = dcutil.synth.images(1, 720, 1280, seed=6)
+    big = netutil.product_forward(net, x)
+    assert big["prob"].shape == (1, 14, 90, 160) and big["next_pred"].shape == (1, 364, 90, 160)
+    for k in big:
+        assert np.isfinite(big[k]).all(), k
+    assert big["prob"].min() > 0 and big["prob"].max() < 1
+    ref = netutil.oracle_forward(path, weights, x[:, :, :256, :256])
+    # this 1-block-per-stage net's receptive field is ~140 px: cells [0, 12) x [0, 12) of the crop only see the crop
+    for k in ("prob", "loc_pred", "next_pred"):
+        assert netutil.max_err(big[k][:, :, :12, :12], ref[k][:, :, :12, :12]) < 1e-4, k
+
+
 @pytest.mark.parametrize("stages,h,w,n", [((3, 4, 23, 3), 128, 160, 1), ((3, 8, 36, 3), 256, 256, 1)])
 def test_full_depth_nets_match_oracle(tmp_path, stages, h, w, n):
     # config[0]/[1] geometry of BASELINE.json at the oracle's comfortable size: the shipped ResNet-152
