@@ -307,6 +307,7 @@ def main():
         for _ in range(2):
             e2e_step()
         _, e2e_wall_ms = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (e2e_wall_ms / 1e3)     # host wall clock: includes every copy and sync
     # ---- per-step roofline pass (separate from the timed region: events around every step)
     roofline = None
     report = None
