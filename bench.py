@@ -2,7 +2,7 @@
 """bench.py -- DeeperCut forward throughput on B200 (images/s), one process per GPU.
 
   python bench.py --gpus N --steps K --warmup W            the B200-native path (this repo)
-  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU algorithm (oracle) on host cores
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU layers (oracle/_ref) on host cores
 
 A "step" = one Net::Forward over one batch of synthetic images.  Default workload: the shipped
 DeeperCut ResNet-152 deploy net, batch 16 of 3x720x1280 per GPU (BASELINE.json configs[2]; the
@@ -15,7 +15,7 @@ batch, no data-path collective in the device-timed region.
           python/pose/estimate_pose.py:231 -- are read back (D2H); for N > 1 rank 0 owns the global batch
           and NCCL scatters inputs / gathers outputs over NVLink
   roofline  conv_igemm (tcgen05) kernels: algorithmic 2*MAC FLOPs / summed device time of those launches
-  cpu_baseline  the oracle (numpy im2col + OpenBLAS sgemm restatement of the reference CPU path), rank 0, N = 1
+  cpu_baseline  the reference's own CPU layer code (oracle/_ref; numpy port if not built), 1 image, rank 0, N = 1
 """
 import argparse
 import ctypes as C
@@ -110,35 +110,60 @@ def workload_name(args):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def time_cpu_reference(path, x1, warmup, steps):
+    """Times the reference's CPU implementation of the path on ONE image (a bounded sample of the workload).
+    Preferred: oracle/_ref/librefcaffe.so -- the reference's own layer sources compiled from /root/reference
+    (oracle/build_ref.py; im2col + OpenBLAS sgemm with every host thread OpenBLAS takes) -> kind "reference".
+    Fallback when that library was not built: the numpy restatement -> kind "port".
+    -> (seconds per image, cpu_baseline dict without "value")."""
+    import ctypes
+    from oracle import ref_caffe
+    synth = importlib.import_module("deepcut-cnn_b200.synth")
+    H, W = x1.shape[2], x1.shape[3]
+    if ref_caffe.available():
+        net = ref_caffe.RefCaffeNet(open(path).read())
+        from oracle import caffe_ref
+        shapes = caffe_ref.load_net(path).typed_param_shapes()
+        net.set_params(synth.weights(shapes))                   # values do not affect CPU time
+        run = lambda: net.forward({"data": x1}, want=["prob", "loc_pred", "next_pred"])
+        try:
+            cores = int(ctypes.CDLL(ref_caffe.LIB_PATH).openblas_get_num_threads())
+        except Exception:
+            cores = os.cpu_count()
+        kind, how = "reference", "reference CPU layers (oracle/_ref: im2col + OpenBLAS sgemm, %d BLAS threads)" % cores
+    else:
+        from oracle import caffe_ref
+        net = caffe_ref.load_net(path)
+        net.params = synth.weights(net.typed_param_shapes())
+        net.reshape_input("data", x1.shape)
+        run = lambda: net.forward({"data": x1})
+        cores, kind, how = os.cpu_count(), "port", "numpy im2col + OpenBLAS sgemm oracle"
+    for _ in range(warmup):
+        run()
+    t0 = time.time()
+    for _ in range(steps):
+        run()
+    dt = (time.time() - t0) / steps
+    return dt, {"unit": "images/s", "cores": cores, "kind": kind,
+                "sample": "1 image 3x%dx%d per step, %d timed after %d warm-up, %s" % (H, W, steps, warmup, how)}
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path: it cannot be built here (no protobuf/glog/
-    boost/BLAS dev files), so this is the oracle port (numpy im2col + OpenBLAS sgemm), on all
-    host cores.  One step = one image of the workload (a bounded sample); rank 0 only."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores; one step =
+    one image of the workload (a bounded sample); rank 0 only, other ranks exit without work."""
     if rank != 0:
         return
-    import numpy as np
-    from oracle import caffe_ref
     synth = importlib.import_module("deepcut-cnn_b200.synth")
-    ptx = importlib.import_module("deepcut-cnn_b200.prototxt")
     path = build_net_files(args)
-    net = caffe_ref.load_net(path)
-    net.params = synth.weights(net.typed_param_shapes())       # values do not affect CPU time
     x = synth.images(1, args.height, args.width)
-    net.reshape_input("data", x.shape)
-    for _ in range(args.warmup):
-        net.forward({"data": x})
-    t0 = time.time()
-    for _ in range(args.steps):
-        net.forward({"data": x})
-    dt = (time.time() - t0) / args.steps
-    cores = os.cpu_count()
+    dt, base = time_cpu_reference(path, x, args.warmup, args.steps)
     v = 1.0 / dt
+    base["value"] = v
     line = {"impl": "reference", "metric": "part-scoremap images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "sample": "1 image per step on host cores"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "1 image 3x%dx%d per step, numpy im2col + OpenBLAS sgemm oracle" % (args.height, args.width)},
+            "cpu_baseline": base,
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -347,22 +372,11 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.step_report)), exist_ok=True)
             json.dump(report, open(args.step_report, "w"), indent=1)
 
-    # ---- CPU baseline (oracle port), rank 0 at N = 1 only
+    # ---- CPU baseline (oracle/_ref = the reference's CPU layers; numpy port if absent), rank 0 at N = 1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import caffe_ref
-        onet = caffe_ref.load_net(path)
-        onet.params = synth.weights(onet.typed_param_shapes())
-        x1 = x[:1]
-        onet.reshape_input("data", x1.shape)
-        onet.forward({"data": x1})
-        t0 = time.time()
-        reps = 2
-        for _ in range(reps):
-            onet.forward({"data": x1})
-        dt = (time.time() - t0) / reps
-        cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": "1 image 3x%dx%d, %d timed forwards after 1 warm-up, numpy im2col + OpenBLAS sgemm oracle" % (H, W, reps)}
+        dt, cpu_baseline = time_cpu_reference(path, x[:1], 1, 2)
+        cpu_baseline["value"] = 1.0 / dt
 
     if rank == 0:
         line = {"metric": "part-scoremap images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,

@@ -1,8 +1,8 @@
-"""Generates tests/golden/tiny_net.npz: outputs of the CPU oracle for the (1,1,1,1)-stage DeeperCut
-topology at 2x3x64x64 with the seeded calibrated weights.  The reference itself cannot be run in
-this container (no protobuf/glog/boost/BLAS dev files), so the vectors come from the oracle, which
-tests/test_oracle_*.py pin against the reference's own known-answer tests.
-Run from the repo root:  python tests/golden/make_golden.py"""
+"""Generates tests/golden/tiny_net.npz: outputs of THE REFERENCE ITSELF (its CPU layer code compiled from
+/root/reference into oracle/_ref by oracle/build_ref.py) for the (1,1,1,1)-stage DeeperCut topology at
+2x3x64x64 with the seeded calibrated weights.  tests/test_oracle_net.py holds the numpy restatement to these
+vectors; the GPU tests hold the product to them.
+Run from the repo root (needs /root/reference):  python tests/golden/make_golden.py"""
 import os
 import sys
 import tempfile
@@ -19,7 +19,10 @@ if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as tmp:
         path, weights = netutil.build(tmp, (1, 1, 1, 1), 64, 64)
         x = dcutil.synth.images(2, 64, 64, seed=7)
-        out = netutil.oracle_forward(path, weights, x, want={"res2a_relu", "res5a_relu"})
-    out["res2a_relu"] = out["res2a_relu"][:, ::16]       # keep the fixture small
+        assert netutil.reference_available(), "oracle/_ref is not built"
+        # in-place chains: blob "res2a" holds res2a_relu's output after the forward (pycaffe convention)
+        r = netutil.reference_forward(path, weights, x, want=["prob", "loc_pred", "next_pred", "res2a", "res5a"])
+    out = {"prob": r["prob"], "loc_pred": r["loc_pred"], "next_pred": r["next_pred"],
+           "res2a_relu": r["res2a"][:, ::16], "res5a_relu": r["res5a"]}       # keep the fixture small
     np.savez_compressed(os.path.join(HERE, "tiny_net.npz"), **{k: v.astype(np.float32) for k, v in out.items()})
     print({k: (v.shape, float(np.abs(v).mean())) for k, v in out.items()})

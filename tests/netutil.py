@@ -26,6 +26,21 @@ def oracle_forward(path, weights, x, want=None):
     return net.forward({"data": x}, want=want)
 
 
+def reference_available():
+    """oracle/_ref: built here when /root/reference exists, prebuilt on the GPU box."""
+    from oracle import build_ref, ref_caffe
+    build_ref.build()
+    return ref_caffe.available()
+
+
+def reference_forward(path, weights, x, want=None):
+    """The reference's own CPU layer code (oracle/_ref) on the same prototxt + weights."""
+    from oracle import ref_caffe
+    net = ref_caffe.RefCaffeNet(open(path).read())
+    net.set_params(weights)
+    return net.forward({"data": x}, want=want)
+
+
 def product_net(path, weights, device=0):
     caffe = dcutil.caffe_module()
     caffe.set_mode_gpu()

@@ -165,3 +165,20 @@ def test_full_depth_nets_match_oracle(tmp_path, stages, h, w, n):
     errs = _report("ResNet stages %s %dx%d" % (stages, h, w), got, ref)
     assert max(errs.values()) < TOL
     assert 0.01 < got["prob"].min() and got["prob"].max() < 0.99
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 64, 64), (1, 512, 512), (1, 720, 1280)])
+def test_resnet152_matches_the_reference_cpu_code(tmp_path, n, h, w):
+    """The product against THE REFERENCE ITSELF (oracle/_ref: its CPU layer sources compiled from /root/reference,
+    prebuilt library shipped to the GPU box) at BASELINE.json's sizes: configs[0] (1x3x512x512) and one 720p image
+    of configs[2] -- full-size parity, not a size-independent property."""
+    if not netutil.reference_available():
+        pytest.skip("oracle/_ref/librefcaffe.so not built")
+    path, weights = netutil.build(tmp_path, (3, 8, 36, 3), h, w)
+    x = dcutil.synth.images(n, h, w, seed=h + w)
+    ref = netutil.reference_forward(path, weights, x, want=["prob", "loc_pred", "next_pred"])
+    net = netutil.product_net(path, weights)
+    got = netutil.product_forward(net, x)
+    assert net.fused_last_forward, net.fusion_diagnostic
+    errs = _report("ResNet-152 %dx3x%dx%d vs reference CPU code" % (n, h, w), got, ref)
+    assert max(errs.values()) < TOL

@@ -1,7 +1,7 @@
 """Whole-net checks of the oracle: (1) against an INDEPENDENT float64 PyTorch model of the same
 prototxt (F.conv2d / conv_transpose2d / max_pool2d(ceil_mode)) so a mis-reading shared with the
-im2col+GEMM restatement cannot hide -- this covers the three rows the reference's own tests leave
-unpinned (BatchNorm global stats, Crop, end-to-end outputs); (2) against the committed golden vectors."""
+im2col+GEMM restatement cannot hide; (2) against the committed golden vectors, which are outputs of the
+reference's own CPU code (tests/golden/make_golden.py); tests/test_oracle_ref.py runs the live comparison."""
 import os
 
 import numpy as np
@@ -33,4 +33,4 @@ def test_oracle_reproduces_golden_vectors(tmp_path):
     out = netutil.oracle_forward(path, weights, x, want={"res2a_relu", "res5a_relu"})
     out["res2a_relu"] = out["res2a_relu"][:, ::16]
     for k in g.files:
-        assert netutil.max_err(out[k], g[k]) < 1e-5, k
+        assert netutil.max_err(out[k], g[k]) < 5e-5, k      # fp32 summation order (OpenBLAS vs numpy)
