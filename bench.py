@@ -12,8 +12,8 @@ batch, no data-path collective in the device-timed region.
   value   images/s over all ranks, inputs resident in HBM, CUDA events on the forward stream, max over ranks
   e2e     same metric through the Caffe API with HOST buffers: per step the input blob is re-uploaded from
           pinned host memory (H2D) and `prob` + `loc_pred` -- the two blobs the reference's caller reads,
-          python/pose/estimate_pose.py:231 -- are read back (D2H); for N > 1 rank 0 owns the global batch
-          and NCCL scatters inputs / gathers outputs over NVLink
+          python/pose/estimate_pose.py:231 -- are read back (D2H); every rank feeds its own pinned host buffers
+          (--e2e-mode exchange: rank 0 owns the global batch, NCCL scatters inputs / gathers outputs over NVLink)
   roofline  conv_igemm (tcgen05) kernels: algorithmic 2*MAC FLOPs / summed device time of those launches
   cpu_baseline  the reference's own CPU layer code (oracle/_ref; numpy port if not built), 1 image, rank 0, N = 1
 """
@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3"],
                     help="BASELINE.json configs: cfg1 = batch 1 3x512x512, cfg2 = batch 16 3x720x1280 (default), cfg3 = batch 16/GPU 3x512x512")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-mode", default="inflight", choices=["inflight", "exchange"],
+                    help="inflight: every rank feeds its own pinned host buffers (default); exchange (N>1): rank 0 owns the global "
+                         "batch and NCCL scatters inputs / gathers outputs")
     ap.add_argument("--e2e-inflight", type=int, default=2,
                     help="end-to-end leg: requests in flight (Net instances on their own host thread + stream); 1 = strictly serial")
     ap.add_argument("--step-report", default=None, help="write the per-step roofline table to this path")
@@ -274,7 +277,12 @@ def main():
     prob, loc = net.blobs["prob"], net.blobs["loc_pred"]
     h2d = B * 3 * H * W * 4
     d2h = (prob.count + loc.count) * 4
-    if dist is None:
+    exchange = dist is not None and args.e2e_mode == "exchange"
+    if not exchange:
+        # every rank serves its own requests from its own pinned host buffers (one PCIe link per GPU): the data-parallel
+        # deployment of this path.  h2d / d2h below are whole-job bytes per step.
+        h2d, d2h = h2d * world, d2h * world
+
         def e2e_step():
             net.blobs["data"].data          # host write access: the pinned host copy is authoritative again -> H2D next forward
             net.forward()
@@ -289,12 +297,12 @@ def main():
             ex.scatter_into(net.blobs["data"], L, stream)
             net.forward()
             ex.gather_from({"prob": prob, "loc_pred": loc}, L, stream)
-    e2e_mode = "serial"
-    if dist is None and args.e2e_inflight > 1:
+    e2e_mode = "rank 0 owns the global batch: NCCL scatter / gather over NVLink around each forward" if exchange else "serial"
+    if not exchange and args.e2e_inflight > 1:
         # Double-buffered serving through the same public API: a second Net (own host thread, own stream, own arena;
         # weights packed from the same blobs) keeps the GPU busy while the first one's H2D / D2H copies are in flight.
         import threading
-        e2e_mode = "%d requests in flight (one Net per host thread/stream)" % args.e2e_inflight
+        e2e_mode = "%d requests in flight per rank (one Net per host thread/stream), per-rank pinned host buffers" % args.e2e_inflight
         weights = {k: [np.array(b.data) for b in bl] for k, bl in net.params.items()}
         ready = threading.Barrier(args.e2e_inflight + 1)
         go = threading.Barrier(args.e2e_inflight + 1)
@@ -335,7 +343,7 @@ def main():
         for t in threads:
             t.start()
         ready.wait()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.time()
         go.wait()
         done.wait()
@@ -344,6 +352,10 @@ def main():
             t.join()
         if errors:
             raise errors[0]
+        if dist is not None:
+            tmax = torch.tensor([e2e_wall_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            e2e_wall_ms = float(tmax[0])
     else:
         for _ in range(2):
             e2e_step()

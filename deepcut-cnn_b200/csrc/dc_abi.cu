@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "../../include/deepcut_b200.h"
@@ -645,6 +646,149 @@ int dc_pose_from_maps(const float* prob, const float* loc, int n, int joints, in
   if (int rc = ensure_init()) return rc;
   if (!prob || !loc || !out || n <= 0 || joints <= 0 || h <= 0 || w <= 0 || scale == 0.f) return fail(DC_ERR_INVALID, "dc_pose_from_maps: bad arguments");
   dc::pose_from_maps_kernel<<<n * joints, 256, 0, static_cast<cudaStream_t>(stream)>>>(prob, loc, joints, h, w, stride, locref_scale, scale, out);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------ demo pre-processing (estimate_pose.py:83-105)
+namespace {
+// Pillow's resampling table for the bilinear filter over a full axis (Resample.c: precompute_coeffs followed by
+// normalize_coeffs_8bpc), restated: the triangle filter's support widens by the shrink factor, taps are normalised in
+// double precision and rounded to 22-bit fixed point.
+struct ResampleTable {
+  int ksize = 0;
+  std::vector<int> bounds;      // {first, count} per output index
+  std::vector<int> kk;          // [out][ksize]
+};
+
+ResampleTable build_resample_table(int in_size, int out_size) {
+  ResampleTable t;
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  t.ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  t.bounds.assign(2 * static_cast<size_t>(out_size), 0);
+  t.kk.assign(static_cast<size_t>(out_size) * t.ksize, 0);
+  const double ss = 1.0 / filterscale;
+  std::vector<double> w(t.ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0) a = -a;
+      w[x] = a < 1.0 ? 1.0 - a : 0.0;
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      const double v = (ww != 0.0 ? w[x] / ww : w[x]) * (1 << 22);
+      t.kk[static_cast<size_t>(xx) * t.ksize + x] = static_cast<int>(v < 0 ? -0.5 + v : 0.5 + v);
+    }
+    t.bounds[2 * xx] = xmin;
+    t.bounds[2 * xx + 1] = xmax;
+  }
+  return t;
+}
+}  // namespace
+
+struct dc_preprocess_plan {
+  int h = 0, w = 0;                 // source image
+  int res_h = 0, res_w = 0;         // rescaled padded image: int((h+64)*scale), int((w+64)*scale)
+  int out_h = 0, out_w = 0;         // net input: ceil(h*scale/8)*8, ceil(w*scale/8)*8
+  int valid_h = 0, valid_w = 0;     // min(out, res)
+  int mid_rows = 0;                 // rows of the horizontal pass the vertical pass reads
+  bool hpass = false, vpass = false;
+  int ksize_x = 0, ksize_y = 0;
+  int *bounds_x = nullptr, *kk_x = nullptr, *bounds_y = nullptr, *kk_y = nullptr;   // device
+};
+
+int dc_preprocess_plan_create(int h, int w, double scale, dc_preprocess_plan** plan) {
+  if (int rc = ensure_init()) return rc;
+  if (!plan || h <= 0 || w <= 0 || !(scale > 0.0)) return fail(DC_ERR_INVALID, "dc_preprocess_plan_create: bad arguments");
+  const int pad = 64, stride = 8;
+  auto p = std::make_unique<dc_preprocess_plan>();
+  p->h = h;
+  p->w = w;
+  p->res_h = static_cast<int>((h + pad) * scale);
+  p->res_w = static_cast<int>((w + pad) * scale);
+  p->out_h = static_cast<int>(std::ceil(static_cast<double>(h) * scale / stride) * stride);
+  p->out_w = static_cast<int>(std::ceil(static_cast<double>(w) * scale / stride) * stride);
+  if (p->res_h <= 0 || p->res_w <= 0 || p->out_h <= 0 || p->out_w <= 0) return fail(DC_ERR_INVALID, "dc_preprocess_plan_create: scale %g leaves no pixels", scale);
+  p->valid_h = std::min(p->out_h, p->res_h);
+  p->valid_w = std::min(p->out_w, p->res_w);
+  p->hpass = p->res_w != w + pad;
+  p->vpass = p->res_h != h + pad;
+  p->mid_rows = p->valid_h;
+  auto upload = [](const std::vector<int>& v, int** dev) -> int {
+    DC_CUDA(cudaMalloc(dev, v.size() * sizeof(int)));
+    DC_CUDA(cudaMemcpy(*dev, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return DC_OK;
+  };
+  int rc = DC_OK;
+  if (p->vpass) {
+    ResampleTable t = build_resample_table(h + pad, p->res_h);
+    p->ksize_y = t.ksize;
+    p->mid_rows = t.bounds[2 * (p->valid_h - 1)] + t.bounds[2 * (p->valid_h - 1) + 1];
+    if ((rc = upload(t.bounds, &p->bounds_y)) || (rc = upload(t.kk, &p->kk_y))) { dc_preprocess_plan_destroy(p.release()); return rc; }
+  }
+  if (p->hpass) {
+    ResampleTable t = build_resample_table(w + pad, p->res_w);
+    p->ksize_x = t.ksize;
+    if ((rc = upload(t.bounds, &p->bounds_x)) || (rc = upload(t.kk, &p->kk_x))) { dc_preprocess_plan_destroy(p.release()); return rc; }
+  }
+  *plan = p.release();
+  return DC_OK;
+}
+
+int dc_preprocess_plan_info(const dc_preprocess_plan* plan, int* out_h, int* out_w, size_t* workspace_bytes) {
+  if (!plan) return fail(DC_ERR_INVALID, "dc_preprocess_plan_info: null plan");
+  if (out_h) *out_h = plan->out_h;
+  if (out_w) *out_w = plan->out_w;
+  if (workspace_bytes) *workspace_bytes = plan->hpass ? static_cast<size_t>(plan->mid_rows) * plan->valid_w * 3 : 0;
+  return DC_OK;
+}
+
+int dc_preprocess_plan_destroy(dc_preprocess_plan* plan) {
+  if (!plan) return DC_OK;
+  cudaFree(plan->bounds_x);
+  cudaFree(plan->kk_x);
+  cudaFree(plan->bounds_y);
+  cudaFree(plan->kk_y);
+  delete plan;
+  return DC_OK;
+}
+
+int dc_preprocess_u8_forward(const dc_preprocess_plan* p, const unsigned char* img, const float* mean3, float* out, void* workspace,
+                             void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!p || !img || !mean3 || !out) return fail(DC_ERR_INVALID, "dc_preprocess_u8_forward: null argument");
+  if (p->hpass && !workspace) return fail(DC_ERR_INVALID, "dc_preprocess_u8_forward: this plan needs a workspace (dc_preprocess_plan_info)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned char* src = img;
+  if (p->hpass) {
+    dim3 grid((p->valid_w + 255) / 256, p->mid_rows);
+    dc::preprocess_hpass_kernel<<<grid, 256, 0, st>>>(img, p->h, p->w, p->mid_rows, p->valid_w, reinterpret_cast<const int2*>(p->bounds_x),
+                                                      p->kk_x, p->ksize_x, static_cast<unsigned char*>(workspace));
+    g_launches++;
+    DC_CUDA(cudaGetLastError());
+    src = static_cast<const unsigned char*>(workspace);
+  }
+  dim3 grid((p->out_w + 255) / 256, p->out_h);
+  const int2* by = reinterpret_cast<const int2*>(p->bounds_y);
+#define DC_PRE_FINISH(HP, VP)                                                                                                        \
+  dc::preprocess_finish_kernel<HP, VP><<<grid, 256, 0, st>>>(src, p->h, p->w, p->valid_w, p->valid_h, p->valid_w, by, p->kk_y, p->ksize_y, \
+                                                              mean3[0], mean3[1], mean3[2], out, p->out_h, p->out_w)
+  if (p->hpass && p->vpass) DC_PRE_FINISH(true, true);
+  else if (p->hpass) DC_PRE_FINISH(true, false);
+  else if (p->vpass) DC_PRE_FINISH(false, true);
+  else DC_PRE_FINISH(false, false);
+#undef DC_PRE_FINISH
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;

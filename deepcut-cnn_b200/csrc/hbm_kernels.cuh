@@ -350,4 +350,90 @@ __global__ void __launch_bounds__(256) split_to_nchw_kernel(const __half* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Demo pre-processing on the device (python/pose/estimate_pose.py:83-105): uint8 HWC image -> edge-replicated 64 px
+// below / right -> PIL bilinear rescale (Pillow Resample.c, 8 bits per channel: separable triangle filter, 22-bit
+// fixed-point coefficients, uint8 rounding after EACH pass, horizontal first) -> minus the per-channel mean -> top-left
+// crop (zero fill beyond the rescaled image) as fp32 CHW.  Byte/integer work, HBM-bound and tiny next to the net
+// (a 720p frame is 2.8 MB in, 11 MB out): one thread per output pixel, x fastest, so both passes read and write
+// coalesced rows.  bounds[i] = {first source index, tap count}, kk[i*ksize + k] the integer coefficients
+// (host: build_resample_table in dc_abi.cu).
+// ---------------------------------------------------------------------------------------
+constexpr int kResampleBits = 32 - 8 - 2;
+
+__device__ __forceinline__ int clip8(int v) {
+  v >>= kResampleBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// horizontal pass over the virtual padded image: mid[y][xo][c], y < rows, xo < cols
+__global__ void __launch_bounds__(256) preprocess_hpass_kernel(const unsigned char* __restrict__ img, int h, int w, int rows, int cols,
+                                                               const int2* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                                               unsigned char* __restrict__ mid) {
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (xo >= cols || y >= rows) return;
+  const unsigned char* row = img + static_cast<size_t>(min(y, h - 1)) * w * 3;
+  const int2 b = bounds[xo];
+  int a0 = 1 << (kResampleBits - 1), a1 = a0, a2 = a0;
+  for (int k = 0; k < b.y; ++k) {
+    const int c = kk[xo * ksize + k];
+    const unsigned char* px = row + min(b.x + k, w - 1) * 3;
+    a0 += px[0] * c;
+    a1 += px[1] * c;
+    a2 += px[2] * c;
+  }
+  unsigned char* o = mid + (static_cast<size_t>(y) * cols + xo) * 3;
+  o[0] = static_cast<unsigned char>(clip8(a0));
+  o[1] = static_cast<unsigned char>(clip8(a1));
+  o[2] = static_cast<unsigned char>(clip8(a2));
+}
+
+// vertical pass (or none) + mean subtraction + crop / zero fill: out[c][yo][xo] fp32.  HP: the source is the horizontal
+// pass's output `mid` [.][cols][3]; otherwise the virtual padded image itself.  VP: apply the vertical taps.
+template <bool HP, bool VP>
+__global__ void __launch_bounds__(256) preprocess_finish_kernel(const unsigned char* __restrict__ src, int h, int w, int cols, int valid_h,
+                                                                int valid_w, const int2* __restrict__ bounds, const int* __restrict__ kk,
+                                                                int ksize, float m0, float m1, float m2, float* __restrict__ out, int out_h,
+                                                                int out_w) {
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yo = blockIdx.y;
+  if (xo >= out_w || yo >= out_h) return;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+  if (yo < valid_h && xo < valid_w) {
+    auto pixel = [&](int y) -> const unsigned char* {
+      if (HP) return src + (static_cast<size_t>(y) * cols + xo) * 3;
+      return src + (static_cast<size_t>(min(y, h - 1)) * w + min(xo, w - 1)) * 3;
+    };
+    int a0, a1, a2;
+    if (VP) {
+      const int2 b = bounds[yo];
+      a0 = a1 = a2 = 1 << (kResampleBits - 1);
+      for (int k = 0; k < b.y; ++k) {
+        const int c = kk[yo * ksize + k];
+        const unsigned char* px = pixel(b.x + k);
+        a0 += px[0] * c;
+        a1 += px[1] * c;
+        a2 += px[2] * c;
+      }
+      a0 = clip8(a0);
+      a1 = clip8(a1);
+      a2 = clip8(a2);
+    } else {
+      const unsigned char* px = pixel(yo);
+      a0 = px[0];
+      a1 = px[1];
+      a2 = px[2];
+    }
+    v0 = static_cast<float>(a0) - m0;
+    v1 = static_cast<float>(a1) - m1;
+    v2 = static_cast<float>(a2) - m2;
+  }
+  const size_t plane = static_cast<size_t>(out_h) * out_w;
+  const size_t o = static_cast<size_t>(yo) * out_w + xo;
+  out[o] = v0;
+  out[plane + o] = v1;
+  out[2 * plane + o] = v2;
+}
+
 }  // namespace dc

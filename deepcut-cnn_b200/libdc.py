@@ -62,6 +62,10 @@ _SIGS = {
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dc_pose_from_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                     C.c_void_p, C.c_void_p]),
+    "dc_preprocess_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_void_p)]),
+    "dc_preprocess_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "dc_preprocess_u8_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dc_preprocess_plan_destroy": (C.c_int, [C.c_void_p]),
     "dc_nchw_to_split": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dc_split_to_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dc_bn_forward_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

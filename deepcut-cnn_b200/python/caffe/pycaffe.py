@@ -67,6 +67,10 @@ class Blob(object):
     def gpu_data_ptr(self):
         return check_ptr(lib.caffe_blob_gpu_data(self._h))
 
+    def mutable_gpu_data_ptr(self):
+        """Blob::mutable_gpu_data(): the device copy becomes the authoritative one (syncedmem.cpp:125-129)."""
+        return check_ptr(lib.caffe_blob_mutable_gpu_data(self._h))
+
 
 class _BlobArray(np.ndarray):
     """ndarray view that keeps its Blob (hence the C++ shared_ptr) alive."""

@@ -156,6 +156,17 @@ int dc_head_finish(const float* col, long long ldcol, int col_row0, const float*
  * that cell.  out: fp32 [n][5][joints] = {x, y, confidence, offset_y, offset_x} exactly as the demo lays them out. */
 int dc_pose_from_maps(const float* prob, const float* loc, int n, int joints, int h, int w, float stride,
                       float locref_scale, float scale, float* out, void* stream);
+/* Demo pre-processing on the device (python/pose/estimate_pose.py:83-105): uint8 [h][w][3] image (device memory; BGR in
+ * the demo) -> 64 px edge-replicated below/right (:90-96) -> scipy.misc.imresize(image, scale, 'bilinear') (:98) == Pillow's
+ * 8-bit bilinear resample, bit-exact -> minus mean3 per channel (:99) -> top-left crop / zero fill to the net input
+ * (:84-88,101-105) as fp32 [3][out_h][out_w] -- the `data` blob's layout (:225-227).  A plan is immutable after create and
+ * owns only its coefficient tables; the caller owns image, output and workspace.  mean3 is read on the host. */
+typedef struct dc_preprocess_plan dc_preprocess_plan;
+int dc_preprocess_plan_create(int h, int w, double scale, dc_preprocess_plan** plan);
+int dc_preprocess_plan_info(const dc_preprocess_plan* plan, int* out_h, int* out_w, size_t* workspace_bytes);
+int dc_preprocess_u8_forward(const dc_preprocess_plan* plan, const unsigned char* img, const float* mean3, float* out,
+                             void* workspace, void* stream);
+int dc_preprocess_plan_destroy(dc_preprocess_plan* plan);
 /* Blob materialisation: fp32 NCHW <-> split NHWC. */
 int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream);
 int dc_split_to_nchw(const void* x, int n, int c, int h, int w, float* out, void* stream);
