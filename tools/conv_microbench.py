@@ -71,3 +71,10 @@ if __name__ == "__main__":
         run(16, 45, 80, 512, 512, 3, 2, 2, 0, 0)
         run(16, 90, 160, 128, 512, 1, 0, 1, 1, 0)
         run(16, 180, 320, 64, 256, 1, 0, 1, 1, 0)
+    elif args.set == "res2":
+        run(16, 180, 320, 64, 64, 3, 1, 1, 0, 0)
+        run(16, 180, 320, 64, 64, 1, 0, 1, 0, 0)
+        run(16, 180, 320, 256, 64, 1, 0, 1, 0, 0)
+        run(16, 180, 320, 64, 256, 1, 0, 1, 0, 0)
+        run(16, 90, 160, 128, 128, 3, 1, 1, 0, 0)
+        run(16, 90, 160, 512, 128, 1, 0, 1, 0, 0)
