@@ -194,18 +194,24 @@ struct Matcher {
     if (conv->num_output() % 32 != 0) return Fail("convolution " + lname + ": cout not a multiple of 32");
     if (k * k > 9) return Fail("convolution " + lname + ": more than 9 taps");
     if (conv->bias_term() && (bn >= 0 || sc >= 0)) return Fail("convolution " + lname + ": bias followed by BatchNorm");
+    int conv_stride = 1;
     if (s != 1) {
       if (!(k == 1 && p == 0)) return Fail("convolution " + lname + ": stride > 1 only for 1x1 pad 0");
+      // default: the conv reads every s-th pixel itself (TMA traversal stride); DC_TMA_STRIDE=0 gathers first
+      static const bool tma_stride = [] { const char* e = getenv("DC_TMA_STRIDE"); return !(e && e[0] == '0'); }();
       const std::pair<int, int> key(in->id, s);
-      if (!subsampled.count(key)) {
+      if (tma_stride && s <= 8) {
+        conv_stride = s;
+      } else if (!subsampled.count(key)) {
         FusedPlan::Tensor* g = NewInternal(FusedPlan::Tensor::kSplit, in->n, in->c, (in->h - 1) / s + 1, (in->w - 1) / s + 1);
         FusedPlan::Step* ss = AddStep(FusedPlan::Step::kSubsample, lname + "/gather");
         ss->in = in; ss->out = g; ss->stride = s;
         subsampled[key] = g;
       }
-      in = subsampled[key];
+      if (conv_stride == 1) in = subsampled[key];
     }
     FusedPlan::Step* st = AddStep(FusedPlan::Step::kConvBN, lname);
+    st->stride = conv_stride;
     st->in = in; st->out = out; st->conv_layer = i; st->bn_layer = bn; st->scale_layer = sc; st->relu = rl >= 0;
     st->kh = st->kw = k; st->pad = p; st->dil = d; st->cout = conv->num_output();
     out->kind = FusedPlan::Tensor::kSplit;
@@ -733,6 +739,7 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
         a.out_f32_rows = st->type == Step::kHeadGemm ? 2 : 0;
         a.ldc = st->out->ld;
         a.out = st->out->ptr;
+        a.stride = st->type == Step::kConvBN ? st->stride : 1;
         DC_CHECK(dc_conv_forward(&a, stream));
         break;
       }
@@ -787,7 +794,7 @@ std::vector<FusedPlan::StepInfo> FusedPlan::LastStepInfo() {
       case Step::kConvBN: {
         const double K = static_cast<double>(st->kh) * st->kw * st->in->c;
         si.flops = 2.0 * st->out->elems() * K;
-        si.bytes = tbytes(st->in) + tbytes(st->out) + tbytes(st->in2) + 4.0 * K * st->cout;
+        si.bytes = tbytes(st->in) / (static_cast<double>(st->stride) * st->stride) + tbytes(st->out) + tbytes(st->in2) + 4.0 * K * st->cout;
         break;
       }
       case Step::kHeadGemm: {

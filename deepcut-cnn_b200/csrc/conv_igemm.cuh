@@ -61,6 +61,7 @@ struct ConvParams {
   int relu;
   int out_mode;
   int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
+  int in_stride;            // spatial stride of a 1x1 conv (the A map traverses W and H with this element stride); >= 1
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2 MMA with M = 256)
@@ -153,7 +154,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int img = mt / p.tiles_y;
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN + cta_rank * Cfg::kBRows;
         for (int t = 0; t < p.ntaps; ++t) {
-          const int ix = x0 + p.tap_dx[t], iy = y0 + p.tap_dy[t];
+          const int ix = x0 * p.in_stride + p.tap_dx[t], iy = y0 * p.in_stride + p.tap_dy[t];
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;

@@ -112,12 +112,13 @@ void pack_row(int K, Get get, uint16_t* hi, uint16_t* lo, float* rowscale) {
 
 int tile_n_for(int cout) { return cout > 64 ? 128 : 64; }
 
-int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw, int th) {
+int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw, int th, int stride = 1) {
   const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, 2};
   const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
                                  (cuuint64_t)n * h * w * c * 2};
-  const cuuint32_t box[5] = {(cuuint32_t)dc::kBK, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
-  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  // traversal stride s: the box spans tw*s x th*s input pixels of which every s-th is loaded (tw x th rows of smem)
+  const cuuint32_t box[5] = {(cuuint32_t)dc::kBK, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), 1, 1};
+  const cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -465,8 +466,12 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   if (a->cin % dc::kBK != 0) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: cin=%d is not a multiple of 64", a->cin);
   if (a->kh * a->kw > dc::kMaxTaps) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: %dx%d filter exceeds 9 taps", a->kh, a->kw);
   if (!a->out_f32_rows && a->cout % 32 != 0) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: cout=%d must be a multiple of 32 for split output", a->cout);
-  const int ho = a->h + 2 * a->pad - (a->dilation * (a->kh - 1) + 1) + 1;
-  const int wo = a->w + 2 * a->pad - (a->dilation * (a->kw - 1) + 1) + 1;
+  const int stride = a->stride > 1 ? a->stride : 1;
+  if (stride > 1 && !(a->kh == 1 && a->kw == 1 && a->pad == 0 && !a->out_f32_rows))
+    return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: stride %d only for 1x1 pad 0 convolutions with split output", stride);
+  if (stride > 8) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: stride %d exceeds the TMA traversal stride limit (8)", stride);
+  const int ho = (a->h + 2 * a->pad - (a->dilation * (a->kh - 1) + 1)) / stride + 1;      // conv_layer.cpp:17-19
+  const int wo = (a->w + 2 * a->pad - (a->dilation * (a->kw - 1) + 1)) / stride + 1;
   if (ho <= 0 || wo <= 0) return fail(DC_ERR_INVALID, "dc_conv_forward: empty output");
   const int bn = tile_n_for(a->cout);
   const int rows = dc_packed_rows(a->cout);
@@ -481,7 +486,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   dc::ConvParams p;
   memset(&p, 0, sizeof(p));
   int n = a->n, h = a->h, w = a->w;
-  const bool pointwise = (a->kh == 1 && a->kw == 1 && a->pad == 0);
+  const bool pointwise = (a->kh == 1 && a->kw == 1 && a->pad == 0 && stride == 1);
   int out_h = ho, out_w = wo;
   if (pointwise) {   // a 1x1 conv is a plain GEMM over all pixels: flatten so tiles never straddle rows
     w = n * h * w; h = 1; n = 1;
@@ -499,9 +504,11 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   long long best = -1;
   for (int i = 0; i < 5; ++i) {
     const int tw = cand[i][0], th = cand[i][1];
+    if (tw * stride > 256 || th * stride > 256) continue;        // TMA box extent limit
     const long long area = static_cast<long long>((out_w + tw - 1) / tw) * tw * ((out_h + th - 1) / th) * th;
     if (best < 0 || area < best) { best = area; p.TW = tw; p.TH = th; }
   }
+  p.in_stride = stride;
   for (p.log2_tw = 0; (1 << p.log2_tw) < p.TW; ++p.log2_tw) {}
   p.tiles_x = (out_w + p.TW - 1) / p.TW;
   p.tiles_y = (out_h + p.TH - 1) / p.TH;
@@ -520,7 +527,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
-  if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH)) return rc;
+  if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH, stride)) return rc;
   if (!a->out_f32_rows) {
     // output geometry as the kernel indexes it (flattened for 1x1): [n][out_h][out_w][cout]
     if (int rc = encode_out_map(&to, a->out, n, out_h, out_w, a->cout, p.TW)) return rc;
@@ -553,6 +560,7 @@ int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packe
   memset(&p, 0, sizeof(p));
   p.H = h2; p.W = w2; p.Ho = h2; p.Wo = w2; p.Cout = 64; p.Cin = 64;
   p.ntaps = 4;
+  p.in_stride = 1;
   for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t - 2; p.tap_dx[t] = 0; }
   const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
   long long best = -1;
@@ -608,9 +616,13 @@ int dc_maxpool_forward(const void* x, int n, int h, int w, int c, int kernel, in
   if (!x || !out || c % 8 != 0) return fail(DC_ERR_INVALID, "dc_maxpool_forward: bad arguments (c must be a multiple of 8)");
   const int ho = dc_pool_out_size(h, kernel, stride), wo = dc_pool_out_size(w, kernel, stride);
   const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
-  dc::maxpool_split_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<long long>(n) * h * w * c, static_cast<__half*>(out),
-      static_cast<long long>(n) * ho * wo * c, n, h, w, c, ho, wo, kernel, stride);
+  if (kernel < 1 || stride < 1 || h < 1 || w < 1) return fail(DC_ERR_INVALID, "dc_maxpool_forward: bad geometry");
+  const __half* xi = static_cast<const __half*>(x);
+  __half* xo = static_cast<__half*>(out);
+  const long long ip = static_cast<long long>(n) * h * w * c, op = static_cast<long long>(n) * ho * wo * c;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kernel == 3) dc::maxpool_split_kernel<3><<<ew_grid(total), 256, 0, st>>>(xi, ip, xo, op, n, h, w, c, ho, wo, kernel, stride);
+  else dc::maxpool_split_kernel<0><<<ew_grid(total), 256, 0, st>>>(xi, ip, xo, op, n, h, w, c, ho, wo, kernel, stride);
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
@@ -633,9 +645,19 @@ int dc_head_finish(const float* col, long long ldcol, int col_off, const float* 
                    float* out, int n, int cout, int h, int w, int ho, int wo, int sigmoid, void* stream) {
   if (int rc = ensure_init()) return rc;
   if (!col || !skip || !out) return fail(DC_ERR_INVALID, "dc_head_finish: null argument");
-  const dim3 grid(static_cast<unsigned>(n) * cout, static_cast<unsigned>((ho * wo + 1023) / 1024));
-  dc::head_finish_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      col, ldcol, col_off, skip, ldskip, skip_off, out, n, cout, h, w, ho, wo, sigmoid);
+  if (n <= 0 || cout <= 0 || h <= 0 || w <= 0 || ho <= 0 || wo <= 0 || ho > 2 * h + 1 || wo > 2 * w + 1)
+    return fail(DC_ERR_INVALID, "dc_head_finish: bad geometry (%dx%d -> %dx%d)", h, w, ho, wo);
+  const int cells = ((ho + 1) / 2) * ((wo + 1) / 2);
+  const dim3 grid(static_cast<unsigned>(n) * cout, static_cast<unsigned>((cells + 255) / 256));
+  // float2 rows: even width, even plane strides, 8-byte-aligned bases
+  const bool vec = (wo % 2 == 0) && (ldskip % 2 == 0) && (reinterpret_cast<uintptr_t>(out) % 8 == 0) &&
+                   (reinterpret_cast<uintptr_t>(skip) % 8 == 0) && ((static_cast<long long>(ho) * wo) % 2 == 0);
+  if (vec)
+    dc::head_finish_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(col, ldcol, col_off, skip, ldskip, skip_off, out, n,
+                                                                                       cout, h, w, ho, wo, sigmoid);
+  else
+    dc::head_finish_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(col, ldcol, col_off, skip, ldskip, skip_off, out, n,
+                                                                                        cout, h, w, ho, wo, sigmoid);
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;

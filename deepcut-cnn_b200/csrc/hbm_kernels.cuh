@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__
 // output pixel x 8 channels (128-bit loads of hi and lo).  The winner's (hi, lo) pair is
 // copied verbatim, so the result is bit-identical to pooling the joined values.
 // ---------------------------------------------------------------------------------------
+// KT > 0: compile-time window (the net's 3x3) -- all KT*KT*2 128-bit loads are issued before the first compare, so a
+// thread keeps 18 loads in flight instead of 2 (the runtime-k loop is latency-bound at ~50 % of the copy bandwidth).
+template <int KT>
 __global__ void __launch_bounds__(256) maxpool_split_kernel(const __half* __restrict__ in, long long in_plane,
                                                             __half* __restrict__ out, long long out_plane, int N,
                                                             int H, int W, int C, int Ho, int Wo, int k, int s) {
@@ -174,24 +177,45 @@ __global__ void __launch_bounds__(256) maxpool_split_kernel(const __half* __rest
     const int oy = static_cast<int>(pidx % Ho);
     const int n = static_cast<int>(pidx / Ho);
     const int y0 = oy * s, x0 = ox * s;
-    const int y1 = min(y0 + k, H), x1 = min(x0 + k, W);
     float best[8];
     __half bh[8], bl[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { best[e] = -3.402823466e+38f; bh[e] = __float2half(0.f); bl[e] = __float2half(0.f); }
-    for (int y = y0; y < y1; ++y)
-      for (int xx = x0; xx < x1; ++xx) {
-        const long long off = ((static_cast<long long>(n) * H + y) * W + xx) * C + g * 8;
-        const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(in + off));
-        const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(in + in_plane + off));
-        const __half* hh = reinterpret_cast<const __half*>(&h4);
-        const __half* ll = reinterpret_cast<const __half*>(&l4);
+    auto consider = [&](const uint4& h4, const uint4& l4) {
+      const __half* hh = reinterpret_cast<const __half*>(&h4);
+      const __half* ll = reinterpret_cast<const __half*>(&l4);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float v = join_f16(hh[e], ll[e]);
-          if (v > best[e]) { best[e] = v; bh[e] = hh[e]; bl[e] = ll[e]; }
-        }
+      for (int e = 0; e < 8; ++e) {
+        const float v = join_f16(hh[e], ll[e]);
+        if (v > best[e]) { best[e] = v; bh[e] = hh[e]; bl[e] = ll[e]; }
       }
+    };
+    if constexpr (KT > 0) {
+      constexpr int kWin = KT > 0 ? KT * KT : 1;
+      uint4 vh[kWin], vl[kWin];
+#pragma unroll
+      for (int dy = 0; dy < KT; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < KT; ++dx) {
+          // windows are clipped at the bottom/right edge: clamp the address, skip the compare below
+          const int y = min(y0 + dy, H - 1), xx = min(x0 + dx, W - 1);
+          const long long off = ((static_cast<long long>(n) * H + y) * W + xx) * C + g * 8;
+          vh[dy * KT + dx] = __ldg(reinterpret_cast<const uint4*>(in + off));
+          vl[dy * KT + dx] = __ldg(reinterpret_cast<const uint4*>(in + in_plane + off));
+        }
+#pragma unroll
+      for (int dy = 0; dy < KT; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < KT; ++dx)
+          if (y0 + dy < H && x0 + dx < W) consider(vh[dy * KT + dx], vl[dy * KT + dx]);
+    } else {
+      const int y1 = min(y0 + k, H), x1 = min(x0 + k, W);
+      for (int y = y0; y < y1; ++y)
+        for (int xx = x0; xx < x1; ++xx) {
+          const long long off = ((static_cast<long long>(n) * H + y) * W + xx) * C + g * 8;
+          consider(__ldg(reinterpret_cast<const uint4*>(in + off)), __ldg(reinterpret_cast<const uint4*>(in + in_plane + off)));
+        }
+    }
     const long long ooff = ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + g * 8;
     *reinterpret_cast<uint4*>(out + ooff) = *reinterpret_cast<const uint4*>(bh);
     *reinterpret_cast<uint4*>(out + out_plane + ooff) = *reinterpret_cast<const uint4*>(bl);
@@ -233,38 +257,55 @@ __global__ void __launch_bounds__(256) subsample_split_kernel(const __half* __re
 //   skip + sum_{p,q : (y-p),(x-q) even, in range} col((co,p,q), (n,(y-p)/2,(x-q)/2))  [-> sigmoid]
 // i.e. DeconvolutionLayer col2im (im2col.cu:246-305) + Crop to Ho x Wo at offset 0
 // (crop_layer.cu:9-38) + Eltwise SUM (eltwise_layer.cu:47-53) + Sigmoid (sigmoid_layer.cu:8-24).
-// One thread per output element, x fastest: every read and the write are unit- or 2-strided rows.
+// One thread per INPUT cell (i, j) of the h x w grid = the 2 x 2 output pixels (2i..2i+1, 2j..2j+1) it feeds: the nine
+// col rows are read once each at (i, j) / (i-1, j) / (i, j-1) / (i-1, j-1) -- unit-stride along j across the warp -- and
+// the two output rows leave as float2 (a warp writes 256 contiguous bytes per row).  Per output pixel the taps are
+// summed in (p, q) order, then added to the skip value, like the one-thread-per-pixel formulation it replaces.
 // ---------------------------------------------------------------------------------------
-// grid = (N * Cout, ceil(Ho*Wo / 1024)); a thread handles 4 pixels of one (n, co) plane, 32-bit index math.
+// grid = (N * Cout, ceil(ceil(Ho/2) * ceil(Wo/2) / 256)); VEC: Wo even and 8-byte-aligned rows (float2 path).
+template <bool VEC>
 __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ col, long long ldcol, int col_row0,
                                                           const float* __restrict__ skip, long long ldskip, int skip_row0,
                                                           float* __restrict__ out, int N, int Cout, int h, int w,
                                                           int Ho, int Wo, int do_sigmoid) {
   const int n = blockIdx.x / Cout, co = blockIdx.x % Cout;
   const int plane = Ho * Wo;
+  const int ch = (Ho + 1) >> 1, cw = (Wo + 1) >> 1;
+  const int cell = blockIdx.y * 256 + threadIdx.x;
+  if (cell >= ch * cw) return;
+  const int i = cell / cw, j = cell - i * cw;
   const float* crow = col + (static_cast<long long>(col_row0) + co * 9) * ldcol + static_cast<long long>(n) * h * w;
   const float* srow = skip + (static_cast<long long>(skip_row0) + co) * ldskip + static_cast<long long>(n) * plane;
   float* orow = out + (static_cast<long long>(n) * Cout + co) * plane;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int idx = blockIdx.y * 1024 + it * 256 + threadIdx.x;
-    if (idx >= plane) break;
-    const int y = idx / Wo, x = idx - y * Wo;
-    float up = 0.f;
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const int yy = y - p;
-      if (yy < 0 || (yy & 1) || (yy >> 1) >= h) continue;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int xx = x - q;
-        if (xx < 0 || (xx & 1) || (xx >> 1) >= w) continue;
-        up += __ldg(crow + (p * 3 + q) * ldcol + (yy >> 1) * w + (xx >> 1));
-      }
-    }
-    float v = __ldg(srow + idx) + up;
+  auto tap = [&](int pq, int ii, int jj) -> float {
+    return (ii >= 0 && ii < h && jj >= 0 && jj < w) ? __ldg(crow + pq * ldcol + ii * w + jj) : 0.f;
+  };
+  // (p, q) order within each output pixel
+  const float u00 = ((tap(0, i, j) + tap(2, i, j - 1)) + tap(6, i - 1, j)) + tap(8, i - 1, j - 1);   // (2i,   2j)
+  const float u01 = tap(1, i, j) + tap(7, i - 1, j);                                                  // (2i,   2j+1)
+  const float u10 = tap(3, i, j) + tap(5, i, j - 1);                                                  // (2i+1, 2j)
+  const float u11 = tap(4, i, j);                                                                     // (2i+1, 2j+1)
+  const int y0 = 2 * i, x0 = 2 * j;
+  const bool x1ok = x0 + 1 < Wo, y1ok = y0 + 1 < Ho;
+  auto fin = [&](float s_, float u) -> float {
+    float v = s_ + u;
     if (do_sigmoid) v = 1.f / (1.f + expf(-v));
-    orow[idx] = v;
+    return v;
+  };
+  if (VEC) {      // Wo even => x1ok always
+    const float2 s0 = __ldg(reinterpret_cast<const float2*>(srow + y0 * Wo + x0));
+    *reinterpret_cast<float2*>(orow + y0 * Wo + x0) = make_float2(fin(s0.x, u00), fin(s0.y, u01));
+    if (y1ok) {
+      const float2 s1 = __ldg(reinterpret_cast<const float2*>(srow + (y0 + 1) * Wo + x0));
+      *reinterpret_cast<float2*>(orow + (y0 + 1) * Wo + x0) = make_float2(fin(s1.x, u10), fin(s1.y, u11));
+    }
+  } else {
+    orow[y0 * Wo + x0] = fin(__ldg(srow + y0 * Wo + x0), u00);
+    if (x1ok) orow[y0 * Wo + x0 + 1] = fin(__ldg(srow + y0 * Wo + x0 + 1), u01);
+    if (y1ok) {
+      orow[(y0 + 1) * Wo + x0] = fin(__ldg(srow + (y0 + 1) * Wo + x0), u10);
+      if (x1ok) orow[(y0 + 1) * Wo + x0 + 1] = fin(__ldg(srow + (y0 + 1) * Wo + x0 + 1), u11);
+    }
   }
 }
 

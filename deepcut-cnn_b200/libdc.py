@@ -11,7 +11,7 @@ class ConvArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int),
                 ("cout", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("pad", C.c_int), ("dilation", C.c_int),
                 ("w_packed", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
-                ("relu", C.c_int), ("out_f32_rows", C.c_int), ("ldc", C.c_int), ("out", C.c_void_p)]
+                ("relu", C.c_int), ("out_f32_rows", C.c_int), ("ldc", C.c_int), ("out", C.c_void_p), ("stride", C.c_int)]
 
 
 _SIGS = {

@@ -102,7 +102,7 @@ typedef struct dc_conv_args {
   /* input: split NHWC [2][n][h][w][cin], cin % 64 == 0 */
   const void* x;
   int n, h, w, cin;
-  /* filter geometry; stride must be 1 (stride-2 1x1 convs go through dc_subsample first) */
+  /* filter geometry (stride: last field) */
   int cout, kh, kw, pad, dilation;
   const void* w_packed;      /* device copy of dc_pack_*_weight output, rows = dc_packed_rows(cout) */
   const float* scale;        /* device [dc_packed_rows(cout)]: folded a[c] * rowscale[c] */
@@ -114,6 +114,9 @@ typedef struct dc_conv_args {
                               *    swapped so its rows are Caffe's col-buffer rows, base_conv_layer.cpp:358-365) */
   int ldc;                   /* row stride in floats: mode 1 >= dc_packed_rows(cout); mode 2 >= n*h*w, multiple of 4 */
   void* out;
+  int stride;                /* 0 or 1: unit stride.  > 1 (<= 8): 1x1 pad-0 convolutions with split output only; the A tensor map
+                              * traverses W and H with this element stride, which is what im2col does for the reference's
+                              * strided 1x1 convs (res3a/res4a branch1 + branch2a; im2col.cu:8-39) */
 } dc_conv_args;
 /* Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-24) =
  * im2col_gpu (util/im2col.cu:8-62) + cublasSgemm (util/math_functions.cu:13-27) per image, and the

@@ -21,7 +21,7 @@ def init():
     libdc.check(libdc.lib().dc_init(torch.cuda.current_device()))
 
 
-def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_rows=False):
+def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_rows=False, stride=1):
     """Runs dc_conv_forward on fp32 NCHW numpy inputs; returns fp32 NCHW numpy (or fp32 rows)."""
     L = libdc.lib()
     n, ci, h, wd = x_nchw.shape
@@ -32,8 +32,8 @@ def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_ro
     shift = np.zeros(rows, np.float32)
     scale[:co] = a * rs[:co]
     shift[:co] = b
-    ho = h + 2 * pad - (dil * (kh - 1) + 1) + 1
-    wo = wd + 2 * pad - (dil * (kw - 1) + 1) + 1
+    ho = (h + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1
+    wo = (wd + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1
     xs = dev(dcutil.np_split(x_nchw))
     wp, sc, sh = dev(packed), dev(scale), dev(shift)
     res = dev(dcutil.np_split(residual_nchw)) if residual_nchw is not None else None
@@ -44,7 +44,7 @@ def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_ro
     args = libdc.ConvArgs(x=xs.data_ptr(), n=n, h=h, w=wd, cin=ci, cout=co, kh=kh, kw=kw, pad=pad, dilation=dil,
                           w_packed=wp.data_ptr(), scale=sc.data_ptr(), shift=sh.data_ptr(),
                           residual=res.data_ptr() if res is not None else None, relu=int(relu),
-                          out_f32_rows=int(f32_rows), ldc=rows, out=out.data_ptr())
+                          out_f32_rows=int(f32_rows), ldc=rows, out=out.data_ptr(), stride=stride)
     libdc.check(L.dc_conv_forward(C.byref(args), stream_ptr()))
     torch.cuda.synchronize()
     if f32_rows:

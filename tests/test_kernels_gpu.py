@@ -92,6 +92,29 @@ def test_conv_residual_ragged_channel_tile(co, _gpu):
     assert np.abs(got - ref).max() < 1e-4
 
 
+@pytest.mark.parametrize("n,ci,co,h,w,stride", [(2, 256, 128, 36, 64, 2), (1, 64, 512, 37, 51, 2), (2, 128, 64, 19, 23, 3), (1, 64, 128, 9, 300, 2)])
+def test_strided_pointwise_conv_reads_through_tma_traversal_stride(n, ci, co, h, w, stride, _gpu):
+    """The reference im2col's its strided 1x1 convs (res3a/res4a branch1 + branch2a, base_conv_layer.cpp:109-116); here
+    the A tensor map traverses W and H with the stride.  Odd sizes: the last strided pixel is the image's last row/column."""
+    rng = np.random.default_rng(n * 100 + ci + stride)
+    x = np.maximum(rng.standard_normal((n, ci, h, w)), 0).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, 1, 1)) * 0.05).astype(np.float32)
+    a = rng.uniform(0.5, 1.5, co).astype(np.float32)
+    b = rng.normal(0, 0.1, co).astype(np.float32)
+    got = _gpu.conv_bn(x, wt, a, b, relu=True, stride=stride)
+    ref = np.maximum(caffe_ref.convolution(x, wt, None, stride, 0, 1) * a.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1), 0)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 1e-4
+
+
+def test_strided_conv_rejects_unsupported_geometry(_gpu):
+    L = libdc.lib()
+    args = libdc.ConvArgs(x=1, n=1, h=8, w=8, cin=64, cout=64, kh=3, kw=3, pad=1, dilation=1, w_packed=1, scale=1, shift=1, residual=None,
+                          relu=0, out_f32_rows=0, ldc=0, out=1, stride=2)
+    assert L.dc_conv_forward(C.byref(args), None) != 0
+    assert b"stride" in L.dc_last_error()
+
+
 def test_conv_f32_rows_with_bias_heads(_gpu):
     # merged 1x1 heads: 512 -> 14+28+364 = 406 with bias, fp32 rows out (res3d_* layers)
     rng = np.random.default_rng(8)
@@ -239,11 +262,14 @@ def test_deconv_head_pipeline(_gpu):
     crop_layer.cpp, eltwise_layer.cpp, sigmoid_layer.cpp)."""
     L = libdc.lib()
     rng = np.random.default_rng(13)
-    for (n, h, w) in ((2, 6, 7), (1, 11, 13)):        # n*h*w not a multiple of 128: ragged pixel tiles
+    # n*h*w not a multiple of 128: ragged pixel tiles; (dh, dw): skip map = (2h+dh) x (2w+dw) (the reference's Crop wants
+    # it strictly smaller than the (2h+1) x (2w+1) deconv output) -- even widths take the float2 path, odd ones the scalar
+    for (n, h, w, dh, dw) in ((2, 6, 7, 0, 0), (1, 11, 13, 0, 0), (2, 5, 9, 0, -1), (1, 7, 4, -1, 0), (1, 3, 3, -1, -1), (1, 4, 6, -2, -3)):
         c5, c3 = 256, 128
+        ho, wo = 2 * h + dh, 2 * w + dw
         heads = (("pose", 14, True), ("locref", 28, False), ("next", 100, False))
         x5 = np.maximum(rng.standard_normal((n, c5, h, w)), 0).astype(np.float32)
-        x3 = np.maximum(rng.standard_normal((n, c3, 2 * h, 2 * w)), 0).astype(np.float32)
+        x3 = np.maximum(rng.standard_normal((n, c3, ho, wo)), 0).astype(np.float32)
         wd = [(rng.standard_normal((c5, co, 3, 3)) * 0.05).astype(np.float32) for _, co, _ in heads]
         bd = [rng.normal(0, 0.1, co).astype(np.float32) for _, co, _ in heads]
         ws = [(rng.standard_normal((co, c3, 1, 1)) * 0.05).astype(np.float32) for _, co, _ in heads]
@@ -265,9 +291,9 @@ def test_deconv_head_pipeline(_gpu):
             ref = caffe_ref.eltwise_sum([sk, caffe_ref.crop(up, sk)])
             if sig:
                 ref = caffe_ref.sigmoid(ref)
-            out = torch.zeros((n, co, 2 * h, 2 * w), dtype=torch.float32, device="cuda")
+            out = torch.full((n, co, ho, wo), float("nan"), dtype=torch.float32, device="cuda")
             libdc.check(L.dc_head_finish(col.data_ptr(), ldcol, off * 9, skip.data_ptr(), ldskip, off, out.data_ptr(), n, co, h, w,
-                                         2 * h, 2 * w, int(sig), _gpu.stream_ptr()))
+                                         ho, wo, int(sig), _gpu.stream_ptr()))
             torch.cuda.synchronize()
             assert np.abs(out.cpu().numpy() - ref).max() < 2e-5, name
             off += co
