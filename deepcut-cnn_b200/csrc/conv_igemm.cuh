@@ -182,6 +182,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {             // the leader CTA issues for the whole group
       constexpr uint32_t idesc = umma_idesc_f16(kBM * CG, BN);
+      [[maybe_unused]] constexpr uint32_t idesc_wide = umma_idesc_f16(kBM, 2 * BN);     // CG = 1: fused hi*hi | hi*lo
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -210,13 +211,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               accum = 1;
               umma_f16_2cta(dx, a_lo + adv, b_hi + adv, idesc, 1);
             } else if (p.swap_ab) {
-              umma_f16(d, b_hi + adv, a_hi + adv, idesc, accum);
-              umma_f16(dx, b_hi + adv, a_lo + adv, idesc, accum);
+              // hi*hi and hi*lo share their M-side operand: one MMA with N = 2*BN over the stacked [a_hi; a_lo] rows
+              // (contiguous in the stage) writes main | cross side by side and reads the shared operand once
+              umma_f16(d, b_hi + adv, a_hi + adv, idesc_wide, accum);
               accum = 1;
               umma_f16(dx, b_lo + adv, a_hi + adv, idesc, 1);
             } else {
-              umma_f16(d, a_hi + adv, b_hi + adv, idesc, accum);
-              umma_f16(dx, a_hi + adv, b_lo + adv, idesc, accum);
+              umma_f16(d, a_hi + adv, b_hi + adv, idesc_wide, accum);      // [b_hi; b_lo] rows are contiguous too
               accum = 1;
               umma_f16(dx, a_lo + adv, b_hi + adv, idesc, 1);
             }

@@ -532,13 +532,18 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
     // output geometry as the kernel indexes it (flattened for 1x1): [n][out_h][out_w][cout]
     if (int rc = encode_out_map(&to, a->out, n, out_h, out_w, a->cout, p.TW)) return rc;
   }
-  const bool pair_mode = use_2cta() && a->out_f32_rows != 2 && g_num_sms >= 2;
-  if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair_mode ? bn / 2 : bn)) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool pair = use_2cta() && !p.swap_ab && g_num_sms >= 2;
-  // epilogue-bound layers (short K, wide output: the 1x1 expand convs) get the 16-warp lean epilogue
+  // CTA pairs for the wide 1x1 convs (fewer operand bytes per SM, the lean epilogue); single CTAs with the fused
+  // N = 2*BN MMA (conv_igemm.cuh) for the 3x3 convs and the 64-channel tiles, where they measure 3-15 % faster
+  // (profiles/r1_microbench_wide_mma.txt).  DC_CONV_PAIR_ALL=1 restores pairs everywhere.
+  static const bool pair_all = [] { const char* e = getenv("DC_CONV_PAIR_ALL"); return e && e[0] == '1'; }();
+  static const bool pair_lean_only = [] { const char* e = getenv("DC_CONV_PAIR_LEAN_ONLY"); return e && e[0] == '1'; }();
   static const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
-  const bool lean = lean_on && pair && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res != nullptr && p.ntaps * p.Cin <= 512 && a->cout >= 256;
+  const bool lean_shape = lean_on && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res != nullptr && p.ntaps * p.Cin <= 512 && a->cout >= 256;
+  const bool pair = use_2cta() && !p.swap_ab && g_num_sms >= 2 && (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)));
+  if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair ? bn / 2 : bn)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // epilogue-bound layers (short K, wide output: the 1x1 expand convs) get the 16-warp lean epilogue
+  const bool lean = pair && lean_shape;
   if (lean) return launch_conv<128, 2, 16>(ta, tb, to, p, st);
   if (bn == 128) return pair ? launch_conv<128, 2>(ta, tb, to, p, st) : launch_conv<128, 1>(ta, tb, to, p, st);
   return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
@@ -591,7 +596,8 @@ int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packe
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled(stem windows) failed: %d", (int)r);
   }
-  const bool pair = use_2cta() && g_num_sms >= 2;
+  static const bool pair_all = [] { const char* e = getenv("DC_CONV_PAIR_ALL"); return e && e[0] == '1'; }();
+  const bool pair = use_2cta() && g_num_sms >= 2 && pair_all;       // BN = 64: single CTAs + fused wide MMA
   if (int rc = encode_w_map(&tb, w_packed, 64, 256, pair ? 32 : 64)) return rc;
   if (int rc = encode_out_map(&to, out, n, h2, w2, 64, p.TW)) return rc;
   return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);

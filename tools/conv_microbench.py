@@ -78,3 +78,8 @@ if __name__ == "__main__":
         run(16, 180, 320, 64, 256, 1, 0, 1, 0, 0)
         run(16, 90, 160, 128, 128, 3, 1, 1, 0, 0)
         run(16, 90, 160, 512, 128, 1, 0, 1, 0, 0)
+    elif args.set == "c3":
+        run(16, 180, 320, 64, 64, 3, 1, 1, 0, 0)
+        run(16, 90, 160, 128, 128, 3, 1, 1, 0, 0)
+        run(16, 45, 80, 256, 256, 3, 1, 1, 0, 0)
+        run(16, 45, 80, 512, 512, 3, 2, 2, 0, 0)
