@@ -42,6 +42,10 @@ CONV_CASES = [
     (512, 2048, 1, 0, 1, 11, 9, 1),
     (2048, 512, 1, 0, 1, 11, 9, 1),
     (64, 64, 3, 3, 3, 21, 18, 1),         # dilation 3 (test_im2col_kernel.cu:55-58 fixture)
+    # more work units than SMs with a short last wave (150 / 198 units on 148 SMs); 192 outputs: ragged second channel tile
+    (128, 128, 1, 0, 1, 120, 160, 1),
+    (64, 128, 1, 0, 1, 132, 192, 1),
+    (64, 192, 3, 1, 1, 40, 48, 5),
 ]
 
 
