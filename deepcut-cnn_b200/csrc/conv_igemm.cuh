@@ -85,15 +85,23 @@ struct ConvCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int CG, int EW>
+// SK = 1 ("split-K", the latency regime: fewer work units than SMs): a cluster of S = 2 or 4 CTAs shares ONE unit,
+// CTA r accumulating K-steps [ksteps * r / S, ksteps * (r + 1) / S) into its own TMEM; the peers then add main + cross
+// and push the fp32 partial tile through distributed shared memory into the leader's (by then idle) pipeline stages,
+// one slot per peer, and the leader's epilogue sums own + slot 0 + slot 1 + ... in that fixed order (no atomics:
+// repeated runs are bitwise identical).  The grid is exactly units * S CTAs, so nothing is persistent in this mode.
+template <int BN, int CG, int EW, int SK = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = ConvCfg<BN, CG, EW>;
+  static_assert(SK == 0 || (CG == 1 && EW == 8), "split-K runs on single CTAs with the 8-warp epilogue");
   const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int ksplit = SK ? static_cast<int>(cluster_nctarank()) : 1;
+  const int krank = SK ? static_cast<int>(cluster_ctarank()) : 0;
   // work units: (m-tile group of CG tiles, n-tile); unit u -> n-tile u % n_tiles_n, m-tile CG * (u / n_tiles_n) + rank
-  const int unit_first = CG == 2 ? (blockIdx.x >> 1) : blockIdx.x;
-  const int unit_stride = CG == 2 ? (gridDim.x >> 1) : gridDim.x;
+  const int unit_first = SK ? static_cast<int>(blockIdx.x) / ksplit : (CG == 2 ? (blockIdx.x >> 1) : blockIdx.x);
+  const int unit_stride = SK ? static_cast<int>(gridDim.x) / ksplit : (CG == 2 ? (gridDim.x >> 1) : gridDim.x);
   const int total_units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -111,6 +119,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int kchunks = p.Cin / kBK;
   const int ksteps = p.ntaps * kchunks;
+  const int ks_begin = SK ? ksteps * krank / ksplit : 0;            // this CTA's share of the K loop
+  const int ks_end = SK ? ksteps * (krank + 1) / ksplit : ksteps;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -156,6 +166,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int t = 0; t < p.ntaps; ++t) {
           const int ix = x0 * p.in_stride + p.tap_dx[t], iy = y0 * p.in_stride + p.tap_dy[t];
           for (int kc = 0; kc < kchunks; ++kc) {
+            if (SK && (t * kchunks + kc < ks_begin || t * kchunks + kc >= ks_end)) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             const int kcoord = (t * kchunks + kc) * kBK;
@@ -178,6 +189,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    if (SK) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }     // the epilogue warps' two reduction barriers
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {             // the leader CTA issues for the whole group
@@ -193,7 +205,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 2 * BN);   // main
         const uint32_t dx = d + BN;                                            // cross terms
         uint32_t accum = 0;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -232,6 +244,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       }
     }
+    if (SK) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }
   } else if (EW == 16) {
     // ------------------------------------------------------------ lean epilogue (warps 2..17), split-NHWC only
     // One 32-pixel x 32-channel chunk per warp per tile.  The residual chunk is copied global -> staging by
@@ -404,7 +417,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     };
-    if (p.out_mode == kOutSplitNHWC && p.res != nullptr) prefetch_residual(unit_first, half * 32);
+    if (p.out_mode == kOutSplitNHWC && p.res != nullptr && krank == 0) prefetch_residual(unit_first, half * 32);
+    // split-K: fp32 partial tiles of the peers, slot s = CTA s + 1, [BN columns][128 rows] floats, in the stage memory
+    [[maybe_unused]] const float* slots = reinterpret_cast<const float*>(smem) + row;
+    [[maybe_unused]] auto add_partials = [&](uint32_t (&r)[32], uint32_t (&rx)[32], int c0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(r[j]) + __uint_as_float(rx[j]);
+        for (int s_ = 0; s_ < ksplit - 1; ++s_) t += slots[(s_ * BN + c0 + j) * kBM];
+        r[j] = __float_as_uint(t);
+        rx[j] = 0u;
+      }
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = unit_first; unit < total_units; unit += unit_stride) {
@@ -420,6 +444,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 2 * BN);
+      if constexpr (SK != 0) {
+        static_assert(3 * BN * kBM * 4 <= Cfg::kStages * Cfg::kStageBytes, "three peer slots must fit the pipeline stages");
+        // #1: every CTA of the cluster has seen its own accumulators complete, i.e. all MMAs (the last readers of the
+        // pipeline stages) are done everywhere: the leader's stage memory is free to receive the partial tiles
+        cluster_sync_all();
+        if (krank != 0) {
+          const uint32_t dst = mapa_shared(smem_u32(smem) + static_cast<uint32_t>(((krank - 1) * BN * kBM + row) * 4), 0);
+#pragma unroll 1
+          for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            uint32_t r[32], rx[32];
+            tmem_ld_32x32(taddr + c0, r);
+            tmem_ld_32x32(taddr + BN + c0, rx);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              st_cluster_f32(dst + static_cast<uint32_t>((c0 + j) * kBM * 4), __uint_as_float(r[j]) + __uint_as_float(rx[j]));
+          }
+        }
+        cluster_sync_all();      // #2 (release / acquire at cluster scope): the partial tiles are visible to the leader
+        if (krank != 0) continue;                      // single unit per cluster: the peers are done
+      }
       if (p.out_mode == kOutF32RowsT) {
         // swapped operands: row = weight row (output channel), columns = the tile's 128 pixels
         // (flat 1x1 geometry: pixel = tx * 128 + column).  out[(n0 + row) * ldc + pixel], fp32.
@@ -498,6 +543,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             sh[4 * g] = b4.x; sh[4 * g + 1] = b4.y; sh[4 * g + 2] = b4.z; sh[4 * g + 3] = b4.w;
           }
           tmem_ld_wait();
+          if constexpr (SK != 0) add_partials(r, rx, c0);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]) + __uint_as_float(rx[j]), sc[j], sh[j]);
@@ -553,6 +599,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_32x32(taddr + c0, r);
           tmem_ld_32x32(taddr + BN + c0, rx);
           tmem_ld_wait();
+          if constexpr (SK != 0) add_partials(r, rx, c0);
           if (!valid) continue;
           float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldc + n0 + c0);
 #pragma unroll

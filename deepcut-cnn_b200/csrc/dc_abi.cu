@@ -473,7 +473,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   const int ho = (a->h + 2 * a->pad - (a->dilation * (a->kh - 1) + 1)) / stride + 1;      // conv_layer.cpp:17-19
   const int wo = (a->w + 2 * a->pad - (a->dilation * (a->kw - 1) + 1)) / stride + 1;
   if (ho <= 0 || wo <= 0) return fail(DC_ERR_INVALID, "dc_conv_forward: empty output");
-  const int bn = tile_n_for(a->cout);
+  int bn = tile_n_for(a->cout);
   const int rows = dc_packed_rows(a->cout);
   if (a->out_f32_rows == 1 && a->ldc < rows) return fail(DC_ERR_INVALID, "dc_conv_forward: ldc=%d < packed rows %d", a->ldc, rows);
   if (a->out_f32_rows == 2) {
@@ -513,6 +513,12 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.tiles_x = (out_w + p.TW - 1) / p.TW;
   p.tiles_y = (out_h + p.TH - 1) / p.TH;
   p.n_tiles_m = n * p.tiles_x * p.tiles_y;
+  // Latency regime (a single image, the demo's case): when 128-channel tiles cannot give every other SM a unit, halve
+  // the channel tile.  Twice the CTAs, each streaming 3/4 of the operand bytes per K-chunk; every output element keeps
+  // its own K chain in the same order, so the result is bitwise the same as with 128-channel tiles (the packed rows
+  // are a multiple of 128, hence of 64).  DC_SMALL_GRID_BN64=0 disables.
+  static const bool small_grid_bn64 = [] { const char* e = getenv("DC_SMALL_GRID_BN64"); return !(e && e[0] == '0'); }();
+  if (small_grid_bn64 && bn == 128 && a->out_f32_rows != 2 && static_cast<long long>(p.n_tiles_m) * (rows / 128) * 2 <= g_num_sms) bn = 64;
   p.n_tiles_n = rows / bn;
   p.scale = a->scale; p.shift = a->shift;
   p.res = static_cast<const __half*>(a->residual);
