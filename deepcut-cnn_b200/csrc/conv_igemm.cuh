@@ -86,10 +86,14 @@ struct ConvCfg {
 };
 
 // SK = 1 ("split-K", the latency regime: fewer work units than SMs): a cluster of S = 2 or 4 CTAs shares ONE unit,
-// CTA r accumulating K-steps [ksteps * r / S, ksteps * (r + 1) / S) into its own TMEM; the peers then add main + cross
-// and push the fp32 partial tile through distributed shared memory into the leader's (by then idle) pipeline stages,
-// one slot per peer, and the leader's epilogue sums own + slot 0 + slot 1 + ... in that fixed order (no atomics:
-// repeated runs are bitwise identical).  The grid is exactly units * S CTAs, so nothing is persistent in this mode.
+// CTA r accumulating K-steps [ksteps * r / S, ksteps * (r + 1) / S) into its own TMEM.  Each peer (r > 0) then adds
+// main + cross, writes the fp32 partial tile into its OWN (by then idle) pipeline stages and, once the leader has
+// signalled that its stages are idle too (remote mbarrier arrive), sends it with ONE bulk DSMEM copy
+// (cp.async.bulk.shared::cluster) into slot r - 1 of the leader's stage memory, completing on the leader's mbarrier;
+// the leader's epilogue sums own + slot 0 + slot 1 + ... in that fixed order (no atomics: repeated runs are bitwise
+// identical).  Scalar st.shared::cluster pushes and barrier.cluster syncs measured 6 us + 2 us per launch
+// (profiles/r1_microbench_latency.txt), more than the K loop they saved.  The grid is exactly units * S CTAs, so nothing
+// is persistent in this mode.
 template <int BN, int CG, int EW, int SK = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -114,6 +118,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * kStages;
   uint64_t* tempty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  [[maybe_unused]] uint64_t* red_full = bars + 2 * kStages + 5;    // split-K leader: all peers' partial tiles have landed
+  [[maybe_unused]] uint64_t* peer_go = bars + 2 * kStages + 6;     // split-K peer: the leader's stage memory is idle
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,6 +140,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EW * CG);     // every epilogue warp of every CTA of the group
     }
+    if (SK) {
+      mbar_init(red_full, 1);
+      mbar_init(peer_go, 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -141,7 +151,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all();             // peer barriers are initialised before any remote arrive
+  if (CG == 2 || SK) cluster_sync_all();       // peer barriers are initialised before any remote arrive
   else __syncthreads();
   tc_fence_after();
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the
@@ -189,7 +199,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-    if (SK) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }     // the epilogue warps' two reduction barriers
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {             // the leader CTA issues for the whole group
@@ -244,7 +253,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       }
     }
-    if (SK) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }
   } else if (EW == 16) {
     // ------------------------------------------------------------ lean epilogue (warps 2..17), split-NHWC only
     // One 32-pixel x 32-channel chunk per warp per tile.  The residual chunk is copied global -> staging by
@@ -446,11 +454,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 2 * BN);
       if constexpr (SK != 0) {
         static_assert(3 * BN * kBM * 4 <= Cfg::kStages * Cfg::kStageBytes, "three peer slots must fit the pipeline stages");
-        // #1: every CTA of the cluster has seen its own accumulators complete, i.e. all MMAs (the last readers of the
-        // pipeline stages) are done everywhere: the leader's stage memory is free to receive the partial tiles
-        cluster_sync_all();
-        if (krank != 0) {
-          const uint32_t dst = mapa_shared(smem_u32(smem) + static_cast<uint32_t>(((krank - 1) * BN * kBM + row) * 4), 0);
+        constexpr uint32_t kTileBytes = BN * kBM * 4;
+        // tfull observed: this CTA's MMAs -- the last readers of its pipeline stages -- are done, the stage memory is idle
+        if (krank == 0) {
+          if (warp == 2 && lane == 0) {
+            mbar_expect_tx(red_full, static_cast<uint32_t>(ksplit - 1) * kTileBytes);
+            for (int r_ = 1; r_ < ksplit; ++r_) mbar_arrive_cluster(mapa_shared(smem_u32(peer_go), r_));
+          }
+          mbar_wait(red_full, 0);                      // the bulk copies' complete_tx: slots are visible to generic loads
+        } else {
+          float* mine = reinterpret_cast<float*>(smem) + row;
 #pragma unroll 1
           for (int c0 = half * 32; c0 < BN; c0 += 64) {
             uint32_t r[32], rx[32];
@@ -458,12 +471,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(taddr + BN + c0, rx);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              st_cluster_f32(dst + static_cast<uint32_t>((c0 + j) * kBM * 4), __uint_as_float(r[j]) + __uint_as_float(rx[j]));
+            for (int j = 0; j < 32; ++j) mine[(c0 + j) * kBM] = __uint_as_float(r[j]) + __uint_as_float(rx[j]);
           }
-        }
-        cluster_sync_all();      // #2 (release / acquire at cluster scope): the partial tiles are visible to the leader
-        if (krank != 0) continue;                      // single unit per cluster: the peers are done
+          fence_proxy_async_smem();                    // generic-proxy writes -> visible to the bulk-copy engine
+          named_bar_sync(1, EW * 32);                  // the whole tile is written (epilogue warps only)
+          if (warp == 2 && lane == 0) {
+            mbar_wait_cluster(peer_go, 0);
+            bulk_copy_to_cluster(mapa_shared(smem_u32(smem) + static_cast<uint32_t>(krank - 1) * kTileBytes, 0), smem, kTileBytes,
+                                 mapa_shared(smem_u32(red_full), 0));
+          }
+          continue;                                    // single unit per cluster: the peers are done (they stay resident
+        }                                              // until the final cluster barrier: the copy reads their smem)
       }
       if (p.out_mode == kOutF32RowsT) {
         // swapped operands: row = weight row (output channel), columns = the tile's 128 pixels
@@ -627,7 +645,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  if (CG == 2) cluster_sync_all();             // nobody touches the peer's barriers / TMEM after this
+  if (CG == 2 || SK) cluster_sync_all();       // nobody touches the peer's barriers / TMEM / shared memory after this
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();

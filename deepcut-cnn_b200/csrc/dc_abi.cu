@@ -21,6 +21,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+// largest split-K cluster dc_conv_forward may pick for under-filled grids (1 = never split); DC_SPLIT_K overrides the default
+std::atomic<int> g_split_k_max{[] { const char* e = getenv("DC_SPLIT_K"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }()};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -41,6 +43,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
+// a layer's K loop is shared by a split-K cluster only from this many 64-channel K-steps on (DC_SPLIT_K_MIN_STEPS)
+std::atomic<int> g_split_k_min_steps{[] { const char* e = getenv("DC_SPLIT_K_MIN_STEPS"); const int v = e ? atoi(e) : 36; return v >= 8 ? v : 36; }()};
 bool g_inited = false;
 
 int ensure_init() {
@@ -157,11 +161,14 @@ bool use_pdl() {
   return on;
 }
 
-template <int BN, int CG, int EW = 8>
-int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st) {
+// ksplit > 1 (SK = 1): a cluster of `ksplit` CTAs per work unit, each taking a share of the K loop (conv_igemm.cuh)
+template <int BN, int CG, int EW = 8, int SK = 0>
+int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st,
+                int ksplit = 1) {
   const int units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   int grid = units * CG < g_num_sms ? units * CG : g_num_sms;
   if (CG == 2) grid &= ~1;
+  if (SK) grid = units * ksplit;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -175,19 +182,46 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     attrs[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (CG == 2) {
+  if (CG == 2 || SK) {
     attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = 2;
+    attrs[na].val.clusterDim.x = SK ? ksplit : 2;
     attrs[na].val.clusterDim.y = 1;
     attrs[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG, EW>, ta, tb, to, p));
+  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG, EW, SK>, ta, tb, to, p));
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
+}
+
+// How many split-K clusters of `s` CTAs (one CTA per SM: ~224 KB of shared memory each) the device keeps resident at once:
+// GPCs whose SM count is not a multiple of `s` strand SMs, so this is less than num_sms / s.  A split grid must fit in
+// one wave, otherwise splitting only adds a second wave.
+template <int BN>
+int max_split_clusters(int s) {
+  static std::atomic<int> cache[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};
+  if (s < 2 || s > 4) return 0;
+  int n = cache[s].load();
+  if (n >= 0) return n;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(g_num_sms / s * s);
+  cfg.blockDim = dim3(dc::conv_threads(8));
+  cfg.dynamicSmemBytes = dc::ConvCfg<BN, 1, 8>::kSmemBytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = s;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, dc::conv_igemm_kernel<BN, 1, 8, 1>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[s].store(n);
+  return n;
 }
 
 // CTA-pair (cta_group::2) kernels for the pixel-major modes; DC_CONV_2CTA=0 falls back to single CTAs.
@@ -207,6 +241,18 @@ int ew_grid(long long total) {
 extern "C" {
 
 int dc_version(void) { return 100; }
+int dc_set_split_k(int max_split) {
+  if (max_split != 1 && max_split != 2 && max_split != 4) return fail(DC_ERR_INVALID, "dc_set_split_k: %d is not 1, 2 or 4", max_split);
+  g_split_k_max.store(max_split);
+  return DC_OK;
+}
+int dc_get_split_k(void) { return g_split_k_max.load(); }
+int dc_set_split_k_min_steps(int min_ksteps) {
+  if (min_ksteps < 8) return fail(DC_ERR_INVALID, "dc_set_split_k_min_steps: %d < 8 (every CTA of a 4-way split needs K-steps)", min_ksteps);
+  g_split_k_min_steps.store(min_ksteps);
+  return DC_OK;
+}
+int dc_get_split_k_min_steps(void) { return g_split_k_min_steps.load(); }
 const char* dc_last_error(void) { return g_err; }
 long long dc_launch_count(void) { return g_launches.load(); }
 
@@ -244,6 +290,8 @@ int dc_init(int device) {
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 2, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2, 16>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 1, 8>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 1, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::kC1SmemFloats * 4));
   g_inited = true;
   return DC_OK;
@@ -545,9 +593,21 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   static const bool pair_lean_only = [] { const char* e = getenv("DC_CONV_PAIR_LEAN_ONLY"); return e && e[0] == '1'; }();
   static const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
   const bool lean_shape = lean_on && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res != nullptr && p.ntaps * p.Cin <= 512 && a->cout >= 256;
-  const bool pair = use_2cta() && !p.swap_ab && g_num_sms >= 2 && (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)));
+  // Still fewer units than a quarter / half of the SMs and a K loop worth sharing (>= 16 K-steps: the exchange costs about
+  // as much as 4 of them, profiles/r1_microbench_latency.txt): split-K clusters of 4 / 2 CTAs per unit.  The summation order over K changes (S partial chains added in rank order), so results differ
+  // from the unsplit kernel by fp32 rounding; it is a pure function of the launch geometry, hence still deterministic.
+  // dc_set_split_k(1) / DC_SPLIT_K=1 disables.
+  int ksplit = 1;
+  if (p.out_mode != dc::kOutF32RowsT) {
+    const long long units = static_cast<long long>(p.n_tiles_m) * p.n_tiles_n;
+    const int ksteps = p.ntaps * (a->cin / dc::kBK);
+    for (int s = 4; s >= 2; s -= 2)
+      if (s <= g_split_k_max.load() && ksteps >= g_split_k_min_steps.load() && units <= (bn == 128 ? max_split_clusters<128>(s) : max_split_clusters<64>(s))) { ksplit = s; break; }
+  }
+  const bool pair = ksplit == 1 && use_2cta() && !p.swap_ab && g_num_sms >= 2 && (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)));
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair ? bn / 2 : bn)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ksplit > 1) return bn == 128 ? launch_conv<128, 1, 8, 1>(ta, tb, to, p, st, ksplit) : launch_conv<64, 1, 8, 1>(ta, tb, to, p, st, ksplit);
   // epilogue-bound layers (short K, wide output: the 1x1 expand convs) get the 16-warp lean epilogue
   const bool lean = pair && lean_shape;
   if (lean) return launch_conv<128, 2, 16>(ta, tb, to, p, st);

@@ -47,6 +47,10 @@ _SIGS = {
     "dc_pack_deconv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dc_pack_conv1_weight": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dc_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "dc_set_split_k": (C.c_int, [C.c_int]),
+    "dc_get_split_k": (C.c_int, []),
+    "dc_set_split_k_min_steps": (C.c_int, [C.c_int]),
+    "dc_get_split_k_min_steps": (C.c_int, []),
     "dc_conv1_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "dc_conv1_tc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -125,6 +125,18 @@ typedef struct dc_conv_args {
  * Also serves DeconvolutionLayer's GEMM (base_conv_layer.cpp:351-367) with kh=kw=1 and a
  * dc_pack_deconv_weight matrix (out_f32_rows = 1). */
 int dc_conv_forward(const dc_conv_args* args, void* stream);
+/* Latency regime (one image; the reference's demo runs batch 1, python/pose/estimate_pose.py:224-243): when a layer has
+ * fewer 128-pixel x N-channel work units than SMs, dc_conv_forward first halves the channel tile (bitwise-neutral) and
+ * then shares each unit's K loop among a cluster of up to `max_split` CTAs (split-K, partial tiles reduced through
+ * distributed shared memory in rank order: deterministic, but the fp32 summation order differs from the unsplit kernel).
+ * max_split in {1, 2, 4}; 1 = never split (bitwise batch-independent results at any size).  Default 4 (env DC_SPLIT_K).
+ * Process-wide; takes effect for launches (and CUDA-graph captures) made after the call. */
+int dc_set_split_k(int max_split);
+int dc_get_split_k(void);
+/* A K loop is shared only from `min_ksteps` 64-channel K-steps on (taps * cin / 64; default 36 = a 3x3 convolution over 256
+ * channels, env DC_SPLIT_K_MIN_STEPS): the exchange costs about as much as 8-15 K-steps (profiles/r1_microbench_latency.txt). */
+int dc_set_split_k_min_steps(int min_ksteps);
+int dc_get_split_k_min_steps(void);
 
 /* ---- HBM-bound kernels --------------------------------------------------------------- */
 /* conv1 7x7/2 pad 3 (3->64) + folded BN/Scale + ReLU.  x: fp32 NCHW [n][3][h][w] (the `data` blob);

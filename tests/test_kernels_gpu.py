@@ -81,6 +81,55 @@ def test_conv_residual_add_relu(_gpu):
     assert np.abs(got2 - branch).max() < 1e-4 and (got2 < 0).any()
 
 
+# (cin, cout, k, pad, dil, H, W, N, residual): few work units, long K loops -> dc_conv_forward shares each unit's K loop
+# among a cluster of 4 / 2 CTAs.  res4 / res5 / res3 geometry of one 512x512 image and smaller; ragged tiles included.
+SPLIT_K_CASES = [
+    (256, 256, 3, 1, 1, 32, 32, 1, False),      # res4 2b @512^2: 8 pixel tiles x 4 channel tiles, 36 K-steps -> S = 4
+    (1024, 256, 1, 0, 1, 32, 32, 1, False),     # res4 2a: 16 K-steps -> S = 4
+    (512, 512, 3, 2, 2, 32, 32, 1, False),      # res5 2b dilated: 64 units -> S = 2
+    (2048, 512, 1, 0, 1, 19, 13, 1, True),      # ragged pixel tile + residual + ReLU
+    (128, 128, 3, 1, 1, 21, 17, 2, True),       # 3x3, ragged rectangles, residual
+    (1024, 160, 1, 0, 1, 9, 11, 1, True),       # ragged channel tile (160 of 256 packed rows), 16 K-steps
+]
+
+
+@pytest.mark.parametrize("case", SPLIT_K_CASES)
+def test_split_k_matches_oracle_and_unsplit_kernel(case, _gpu):
+    ci, co, k, pad, dil, h, w, n, with_res = case
+    L = libdc.lib()
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = np.maximum(rng.standard_normal((n, ci, h, w)), 0).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, k, k)) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32)
+    a, b = _bn_params(rng, co)
+    shortcut = rng.standard_normal((n, co, h, w)).astype(np.float32) if with_res else None
+    ref = caffe_ref.convolution(x, wt, None, 1, pad, dil) * a.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1)
+    if with_res:
+        ref = ref + shortcut
+    ref = np.maximum(ref, 0)
+    got = {}
+    try:
+        libdc.check(L.dc_set_split_k_min_steps(16))      # default 36 (where splitting pays); 16 here so every case splits
+        for s in (1, 2, 4):
+            libdc.check(L.dc_set_split_k(s))
+            got[s] = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True, residual_nchw=shortcut)
+            assert np.isfinite(got[s]).all()
+            assert np.abs(got[s] - ref).max() < 1e-4, (s, np.abs(got[s] - ref).max())
+            again = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True, residual_nchw=shortcut)
+            assert np.array_equal(got[s], again), "split %d is not deterministic" % s
+        rows = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=False, f32_rows=True)       # fp32-rows epilogue, split
+        libdc.check(L.dc_set_split_k(1))
+        rows1 = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=False, f32_rows=True)
+    finally:
+        libdc.check(L.dc_set_split_k(4))
+        libdc.check(L.dc_set_split_k_min_steps(36))
+    # the split only re-associates the fp32 sum over K
+    for s in (2, 4):
+        assert np.abs(got[s] - got[1]).max() < 5e-5, (s, np.abs(got[s] - got[1]).max())
+    assert np.abs(rows[:, :co] - rows1[:, :co]).max() < 5e-5
+    assert L.dc_set_split_k(3) != 0 and L.dc_get_split_k() == 4
+    assert L.dc_set_split_k_min_steps(4) != 0 and L.dc_get_split_k_min_steps() == 36
+
+
 @pytest.mark.parametrize("co", [160, 192, 320])      # 320 >= 256 takes the 16-warp lean epilogue
 def test_conv_residual_ragged_channel_tile(co, _gpu):
     # the second 128-channel tile is partly empty; residual prefetch registers of skipped chunks must

@@ -57,6 +57,46 @@ def run(n, h, w, cin, cout, k, pad, dil, residual, mode, iters=20):
           (n, h, w, cin, cout, k, dil, residual, mode, ms * 1e3, fl / ms / 1e9, 3 * fl / ms / 1e9, by / ms / 1e6))
 
 
+def run_latency(n, h, w, cin, cout, k, pad, dil, residual, chain=50, reps=10):
+    """Latency regime: `chain` dependent launches of one small conv captured into a CUDA graph (no host launch cost, programmatic
+    dependent launch between them, every launch waits for its predecessor like consecutive layers do); us per launch."""
+    rows = L.dc_packed_rows(cout)
+    K = k * k * cin
+    x = torch.randn(2, n, h, w, cin, device="cuda").half()
+    wp = torch.randn(2, rows, K, device="cuda").half()
+    sc = torch.ones(rows, device="cuda")
+    sh = torch.zeros(rows, device="cuda")
+    ho, wo = h + 2 * pad - (dil * (k - 1) + 1) + 1, w + 2 * pad - (dil * (k - 1) + 1) + 1
+    res = torch.randn(2, n, ho, wo, cout, device="cuda").half() if residual else None
+    out = torch.empty(2, n, ho, wo, cout, device="cuda", dtype=torch.half)
+    a = libdc.ConvArgs(x=x.data_ptr(), n=n, h=h, w=w, cin=cin, cout=cout, kh=k, kw=k, pad=pad, dilation=dil,
+                       w_packed=wp.data_ptr(), scale=sc.data_ptr(), shift=sh.data_ptr(),
+                       residual=res.data_ptr() if residual else None, relu=1, out_f32_rows=0, ldc=0, out=out.data_ptr())
+    st = C.c_void_p()
+    libdc.check(L.dc_stream_create(C.byref(st)))
+    libdc.check(L.dc_conv_forward(C.byref(a), st))
+    libdc.check(L.dc_stream_sync(st))
+    g = C.c_void_p()
+    libdc.check(L.dc_graph_begin(st))
+    for _ in range(chain):
+        libdc.check(L.dc_conv_forward(C.byref(a), st))
+    libdc.check(L.dc_graph_end(st, C.byref(g)))
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    libdc.check(L.dc_event_create(C.byref(e0)))
+    libdc.check(L.dc_event_create(C.byref(e1)))
+    libdc.check(L.dc_graph_launch(g, st))
+    libdc.check(L.dc_stream_sync(st))
+    libdc.check(L.dc_event_record(e0, st))
+    for _ in range(reps):
+        libdc.check(L.dc_graph_launch(g, st))
+    libdc.check(L.dc_event_record(e1, st))
+    ms = C.c_float()
+    libdc.check(L.dc_event_elapsed_ms(e0, e1, C.byref(ms)))
+    L.dc_graph_destroy(g)
+    print("latency n%d %dx%d %d->%d k%d d%d res=%d split_k<=%d debug=%s : %.2f us / launch" %
+          (n, h, w, cin, cout, k, dil, residual, L.dc_get_split_k(), os.environ.get("DC_SK_DEBUG", "0"), ms.value * 1e3 / (chain * reps)))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--set", default="res4")
@@ -78,6 +118,14 @@ if __name__ == "__main__":
         run(16, 180, 320, 64, 256, 1, 0, 1, 0, 0)
         run(16, 90, 160, 128, 128, 3, 1, 1, 0, 0)
         run(16, 90, 160, 512, 128, 1, 0, 1, 0, 0)
+    elif args.set == "lat":        # one 512x512 image: res4 2b / 2a / 2c, res5 2b / 2a, res3 2b / 2a
+        run_latency(1, 32, 32, 256, 256, 3, 1, 1, 0)
+        run_latency(1, 32, 32, 1024, 256, 1, 0, 1, 0)
+        run_latency(1, 32, 32, 256, 1024, 1, 0, 1, 1)
+        run_latency(1, 32, 32, 512, 512, 3, 2, 2, 0)
+        run_latency(1, 32, 32, 2048, 512, 1, 0, 1, 0)
+        run_latency(1, 64, 64, 128, 128, 3, 1, 1, 0)
+        run_latency(1, 64, 64, 512, 128, 1, 0, 1, 0)
     elif args.set == "c3":
         run(16, 180, 320, 64, 64, 3, 1, 1, 0, 0)
         run(16, 90, 160, 128, 128, 3, 1, 1, 0, 0)
