@@ -62,6 +62,7 @@ struct ConvParams {
   int out_mode;
   int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
   int in_stride;            // spatial stride of a 1x1 conv (the A map traverses W and H with this element stride); >= 1
+  int early_weights;        // request the first stages' weight tiles before the grid dependency resolves (DC_EARLY_WEIGHTS)
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2 MMA with M = 256)
@@ -157,14 +158,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the
   // previous kernel; from here on we read what it wrote.
   pdl_launch_dependents();
-  pdl_wait();
+  if (warp != 0) pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      // Weights do not depend on the predecessor kernel: the weight tiles of this CTA's first K-steps (one per pipeline
+      // stage) are requested BEFORE griddepcontrol.wait, so their HBM latency (a single image re-reads all 251 MB of
+      // packed weights from HBM every forward) overlaps the predecessor's tail; the activation tiles follow after the wait.
+      int npre = 0;
+      if (p.early_weights && unit_first < total_units) {
+        const int n0 = (unit_first % p.n_tiles_n) * BN + cta_rank * Cfg::kBRows;
+        for (int ks = ks_begin; ks < ks_end && npre < kStages; ++ks, ++npre) {
+          uint8_t* sa = smem + npre * Cfg::kStageBytes;
+          if (CG == 2) {
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[npre], 2 * Cfg::kStageBytes);
+            tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0);
+            tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1);
+          } else {
+            mbar_expect_tx(&full_bar[npre], Cfg::kStageBytes);
+            tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0);
+            tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1);
+          }
+        }
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
       for (int unit = unit_first; unit < total_units; unit += unit_stride) {
         const int nt = unit % p.n_tiles_n;
         int mt = (unit / p.n_tiles_n) * CG + cta_rank;    // a phantom tile (mt == n_tiles_m) decodes to img == N: all-OOB boxes
@@ -180,19 +202,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             const int kcoord = (t * kchunks + kc) * kBK;
+            const bool fresh = issued >= npre;      // else: this stage's barrier is armed and its weight tiles are on their way
+            ++issued;
             if (CG == 2) {
               // both CTAs' loads count on the leader's barrier; only the leader arms it (for both halves)
-              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              if (cta_rank == 0 && fresh) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
               tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
               tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
-              tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
-              tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+              if (fresh) {
+                tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
+                tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+              }
             } else {
-              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              if (fresh) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
               tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
               tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
-              tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
-              tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+              if (fresh) {
+                tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
+                tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+              }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }

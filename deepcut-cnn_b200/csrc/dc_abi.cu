@@ -156,6 +156,12 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, long long K, int bn
   return DC_OK;
 }
 
+// conv_igemm requests its first weight tiles before griddepcontrol.wait (DC_EARLY_WEIGHTS=0: after it, like the activations)
+int use_early_weights() {
+  static const int on = [] { const char* e = getenv("DC_EARLY_WEIGHTS"); return e ? atoi(e) : 1; }();
+  return on;
+}
+
 bool use_pdl() {
   static const bool on = [] { const char* e = getenv("DC_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -578,6 +584,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.relu = a->relu;
   p.out_mode = a->out_f32_rows == 2 ? dc::kOutF32RowsT : (a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC);
   p.swap_ab = a->out_f32_rows == 2;
+  p.early_weights = use_early_weights();
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
@@ -650,6 +657,7 @@ int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packe
   p.out_plane = static_cast<long long>(n) * h2 * w2 * 64;
   p.relu = 1;
   p.out_mode = dc::kOutSplitNHWC;
+  p.early_weights = use_early_weights();
 
   // A: overlapping 4-pixel windows of the padded space-to-depth image (W stride = one 16-channel pixel)
   CUtensorMap ta, tb, to;
