@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--e2e-inflight", type=int, default=2,
                     help="end-to-end leg: requests in flight (Net instances on their own host thread + stream); 1 = strictly serial")
     ap.add_argument("--step-report", default=None, help="write the per-step roofline table to this path")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="--impl reference: host seconds the (warmup + steps) samples may take; a step shrinks from one image to its top 1/d")
     return ap.parse_args()
 
 
@@ -113,29 +115,33 @@ def workload_name(args):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def time_cpu_reference(path, x1, warmup, steps):
-    """Times the reference's CPU implementation of the path on ONE image (a bounded sample of the workload).
+def time_cpu_reference(path, x1, warmup, steps, budget_s):
+    """Times the reference's CPU implementation of the path on a BOUNDED SAMPLE of the workload: one image, or -- when
+    (warmup + steps) whole images would not fit `budget_s` seconds of host time -- the top 1/d of one image (a full-width strip;
+    the path is fully convolutional and its CPU cost is linear in the pixel count), counted as 1/d image.
     Preferred: oracle/_ref/librefcaffe.so -- the reference's own layer sources compiled from /root/reference
     (oracle/build_ref.py; im2col + OpenBLAS sgemm with every host thread OpenBLAS takes) -> kind "reference".
     Fallback when that library was not built: the numpy restatement -> kind "port".
-    -> (seconds per image, cpu_baseline dict without "value")."""
+    -> (seconds per IMAGE, cpu_baseline dict without "value", seconds per step, images per step)."""
     import ctypes
     from oracle import ref_caffe
     synth = importlib.import_module("deepcut-cnn_b200.synth")
     H, W = x1.shape[2], x1.shape[3]
+    est_image_s = None
     if ref_caffe.available():
         net = ref_caffe.RefCaffeNet(open(path).read())
         from oracle import caffe_ref
         shapes = caffe_ref.load_net(path).typed_param_shapes()
         net.set_params(synth.weights(shapes))                   # values do not affect CPU time
-        run = lambda: net.forward({"data": x1}, want=["prob", "loc_pred", "next_pred"])
+        forward = lambda x: net.forward({"data": x}, want=["prob", "loc_pred", "next_pred"])
         # OpenBLAS takes every core by default, which is slower than a moderate count on a many-core host (im2col is
         # serial and the per-image GEMMs are small): give the reference its best thread count, picked on a
         # quarter-size image, rather than a handicap.
         blas = ctypes.CDLL(ref_caffe.LIB_PATH)
         try:
             max_threads = int(blas.openblas_get_num_threads())
-            small = synth.images(1, max(64, H // 2), max(64, W // 2))
+            hs, ws = max(64, H // 2), max(64, W // 2)
+            small = synth.images(1, hs, ws)
             best = (None, max_threads)
             for t in sorted({min(max_threads, c) for c in (8, 16, 32, 64, max_threads)}):
                 blas.openblas_set_num_threads(t)
@@ -147,6 +153,7 @@ def time_cpu_reference(path, x1, warmup, steps):
                     best = (dt, t)
             cores = best[1]
             blas.openblas_set_num_threads(cores)
+            est_image_s = best[0] * (H * W) / float(hs * ws)
         except Exception:
             cores = os.cpu_count()
         kind, how = "reference", "reference CPU layers (oracle/_ref: im2col + OpenBLAS sgemm, %d BLAS threads = fastest of 8..all)" % cores
@@ -154,17 +161,28 @@ def time_cpu_reference(path, x1, warmup, steps):
         from oracle import caffe_ref
         net = caffe_ref.load_net(path)
         net.params = synth.weights(net.typed_param_shapes())
-        net.reshape_input("data", x1.shape)
-        run = lambda: net.forward({"data": x1})
+
+        def forward(x):
+            net.reshape_input("data", x.shape)
+            return net.forward({"data": x})
         cores, kind, how = os.cpu_count(), "port", "numpy im2col + OpenBLAS sgemm oracle"
+    # the sample: a whole image if (warmup + steps) of them fit the budget, else the top 1/d of it
+    d = 1
+    if est_image_s is not None:
+        while d < 16 and (warmup + steps) * est_image_s / d > budget_s and H // (2 * d) >= 64:
+            d *= 2
+    rows = H if d == 1 else max(64, (H // d) // 8 * 8)
+    xs = x1[:, :, :rows, :]
+    frac = rows / float(H)
     for _ in range(warmup):
-        run()
+        forward(xs)
     t0 = time.time()
     for _ in range(steps):
-        run()
+        forward(xs)
     dt = (time.time() - t0) / steps
-    return dt, {"unit": "images/s", "cores": cores, "kind": kind,
-                "sample": "1 image 3x%dx%d per step, %d timed after %d warm-up, %s" % (H, W, steps, warmup, how)}
+    what = "1 image 3x%dx%d" % (H, W) if d == 1 else "the top %d rows of one 3x%dx%d image (= %.4f image; CPU cost is linear in pixels)" % (rows, H, W, frac)
+    return dt / frac, {"unit": "images/s", "cores": cores, "kind": kind,
+                       "sample": "%s per step, %d timed after %d warm-up, %s" % (what, steps, warmup, how)}, dt, frac
 
 
 def run_reference(args, rank, world):
@@ -175,13 +193,14 @@ def run_reference(args, rank, world):
     synth = importlib.import_module("deepcut-cnn_b200.synth")
     path = build_net_files(args)
     x = synth.images(1, args.height, args.width)
-    dt, base = time_cpu_reference(path, x, args.warmup, args.steps)
+    dt, base, step_s, per_step = time_cpu_reference(path, x, args.warmup, args.steps, budget_s=args.ref_budget_s)
     v = 1.0 / dt
     base["value"] = v
     line = {"impl": "reference", "metric": "part-scoremap images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sample": "1 image per step on host cores"},
+            "config": {"workload": workload_name(args), "sample": base["sample"].split(" per step")[0] + " per step on host cores",
+                       "images_per_step": per_step},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -403,7 +422,7 @@ def main():
     # ---- CPU baseline (oracle/_ref = the reference's CPU layers; numpy port if absent), rank 0 at N = 1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        dt, cpu_baseline = time_cpu_reference(path, x[:1], 1, 2)
+        dt, cpu_baseline, _, _ = time_cpu_reference(path, x[:1], 1, 2, budget_s=45.0)    # ~10-30 s of timed CPU work
         cpu_baseline["value"] = 1.0 / dt
 
     if rank == 0:
