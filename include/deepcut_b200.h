@@ -83,7 +83,8 @@ int dc_fold_bn_scale(const float* mean_sum, const float* var_sum, float factor, 
 
 /* Rows of the packed weight matrix after padding Cout to the conv kernel's N tile. */
 int dc_packed_rows(int cout);
-/* N tile (out-channels per CTA tile) the conv kernel uses for `cout` output channels. */
+/* N tile (out-channels per CTA tile) the packed weight rows are padded to for `cout` output channels (64 or 128).  A launch
+ * whose grid would be under-filled may run 64-channel tiles over 128-padded rows (same results bitwise). */
 int dc_tile_n(int cout);
 /* Packs a Caffe Convolution weight blob W[cout][cin][kh][kw] (base_conv_layer.cpp:135-140) into the
  * K-major split-fp16 matrix the implicit GEMM reads: packed[2][rows][K], K = (p*kw+q)*cin + ci,
