@@ -15,7 +15,9 @@ batch, no data-path collective in the device-timed region.
           python/pose/estimate_pose.py:231 -- are read back (D2H); every rank feeds its own pinned host buffers
           (--e2e-mode exchange: rank 0 owns the global batch, NCCL scatters inputs / gathers outputs over NVLink)
   roofline  conv_igemm (tcgen05) kernels: algorithmic 2*MAC FLOPs / summed device time of those launches
-  cpu_baseline  the reference's own CPU layer code (oracle/_ref; numpy port if not built), 1 image, rank 0, N = 1
+  cpu_baseline  the reference's own CPU layer code (oracle/_ref; numpy port if not built), a bounded sample (one image or its
+                top 1/d), rank 0, N = 1
+  latency_config  (default workload, N = 1) the same net on ONE 3x512x512 image = BASELINE configs[1], the demo's regime
 """
 import argparse
 import ctypes as C
@@ -45,6 +47,8 @@ def parse_args():
     ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3"],
                     help="BASELINE.json configs: cfg1 = batch 1 3x512x512, cfg2 = batch 16 3x720x1280 (default), cfg3 = batch 16/GPU 3x512x512")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency-config", action="store_true",
+                    help="skip the extra single-image measurement (BASELINE configs[1]: batch 1, 3x512x512) the default workload reports")
     ap.add_argument("--e2e-mode", default="inflight", choices=["inflight", "exchange"],
                     help="inflight: every rank feeds its own pinned host buffers (default); exchange (N>1): rank 0 owns the global "
                          "batch and NCCL scatters inputs / gathers outputs")
@@ -68,7 +72,7 @@ def peaks():
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -79,16 +83,35 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """The sampler is started before the warm-up (nvidia-smi needs ~0.2 s to produce its first row); only rows stamped
+        inside the timed region [t0, t1] (host clock) count.  Fewer than two such rows -> all rows, upper half = under load."""
+        import datetime
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
+        if t0 is not None:
+            inside = []
+            for r in self.rows:
+                try:
+                    ts = datetime.datetime.strptime(r[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except (IndexError, ValueError):
+                    continue
+                if t0 <= ts <= t1:
+                    inside.append(r)
+            if len(inside) >= 2:
+                sm = sorted(int(r[0]) for r in inside if r[0].isdigit())
+                mx = max([int(r[1]) for r in inside if r[1].isdigit()] or [0])
+                reasons = [name for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                           if any(r[3 + i].lower().startswith("active") for r in inside)]
+                return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                        "window": "timed region"}
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
         reasons = []
@@ -279,17 +302,19 @@ def main():
         return float(t[0]), float(t[1])
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     net.forward()                       # builds the plan, packs weights, uploads the input
     assert net.fused_last_forward, "fused plan not active: " + net.fusion_diagnostic
     for _ in range(max(args.warmup, 3) - 1):
         net.forward()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = L.dc_launch_count()
+    t_region0 = time.time()
     dev_ms, wall_ms = timed(net.forward, args.steps)
+    t_region1 = time.time()
     launches = L.dc_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     value = world * B * args.steps / (dev_ms / 1e3)
 
     # ---- end to end through the Caffe API with host buffers
@@ -419,6 +444,26 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.step_report)), exist_ok=True)
             json.dump(report, open(args.step_report, "w"), indent=1)
 
+    # ---- the latency point: BASELINE configs[1] (one 3x512x512 image, what the reference's demo runs), reported beside the
+    # throughput workload; same weights, its own Net / plan / CUDA graph; device-resident, CUDA events, 50 steps after 5
+    latency = None
+    if rank == 0 and world == 1 and (B, H, W) == (16, 720, 1280) and not args.no_latency_config:
+        gen = importlib.import_module("deepcut-cnn_b200.gen_prototxt")
+        lpath = os.path.join(ROOT, "models", "_gen", "bench_resnet%s_512x512_latency.prototxt" % args.model)
+        gen.write(lpath, stages=gen.STAGES_152 if args.model == "152" else gen.STAGES_101, height=512, width=512)
+        lnet = caffe.Net(lpath, caffe.TEST)
+        lnet.set_params({k: [np.array(b.data) for b in bl] for k, bl in net.params.items()})
+        lnet.blobs["data"].reshape(1, 3, 512, 512)
+        lnet.blobs["data"].data[...] = synth.images(1, 512, 512, seed=7)
+        for _ in range(5):
+            lnet.forward()
+        l0 = L.dc_launch_count()
+        lat_ms, _ = timed(lnet.forward, 50)
+        latency = {"workload": "DeeperCut ResNet-%s deploy net, fwd, batch 1, 3x512x512 (BASELINE configs[1])" % args.model,
+                   "ms_per_image": lat_ms / 50, "value": 50 / (lat_ms / 1e3), "unit": "images/s", "steps": 50, "warmup": 5,
+                   "gpu_launches_per_image": int((L.dc_launch_count() - l0) // 50), "split_k_max": int(L.dc_get_split_k())}
+        del lnet
+
     # ---- CPU baseline (oracle/_ref = the reference's CPU layers; numpy port if absent), rank 0 at N = 1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -434,7 +479,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred", "mode": e2e_mode},
-                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency,
                 "wall_ms_per_step": wall_ms / args.steps, "arena_mib": net.arena_bytes >> 20, "weights_mib": net.weight_bytes >> 20}
         print(json.dumps(line))
     if dist is not None:
