@@ -72,6 +72,8 @@ class FusedPlan {
   std::vector<Step*> steps_;
   void* arena_ = nullptr;
   size_t arena_bytes_ = 0;
+  void* splitk_ws_ = nullptr;           // tail of the arena: scratch of the split-K conv launches
+  size_t splitk_ws_bytes_ = 0;
   std::shared_ptr<PlanWeightCache> weights_;
   std::vector<int> split_layers_;     // Split layer ids to alias after a materialised run
   bool materialize_ = false;

@@ -522,8 +522,13 @@ void FusedPlan::PlanMemory() {
     for (Tensor* u : tensors_)
       if (u->bytes && u->last_step == static_cast<int>(s)) release(u->offset, u->bytes);
   }
-  arena_bytes_ = std::max<size_t>(top, 1024);
+  // the tail of the arena is the split-K scratch of this plan's under-filled conv launches (dc_conv_args.splitk_workspace):
+  // one region for the whole plan, the launches that use it are serialised on the plan's stream
+  splitk_ws_bytes_ = dc_splitk_workspace_bytes();
+  const size_t ws_off = AlignUp(std::max<size_t>(top, 1024), 1024);
+  arena_bytes_ = ws_off + splitk_ws_bytes_;
   DC_CHECK(dc_malloc(&arena_, arena_bytes_));
+  splitk_ws_ = static_cast<char*>(arena_) + ws_off;
   for (Tensor* t : tensors_)
     if (t->bytes) t->ptr = static_cast<char*>(arena_) + t->offset;
 }
@@ -740,6 +745,8 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
         a.ldc = st->out->ld;
         a.out = st->out->ptr;
         a.stride = st->type == Step::kConvBN ? st->stride : 1;
+        a.splitk_workspace = splitk_ws_;
+        a.splitk_workspace_bytes = splitk_ws_bytes_;
         DC_CHECK(dc_conv_forward(&a, stream));
         break;
       }

@@ -63,6 +63,7 @@ struct ConvParams {
   int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
   int in_stride;            // spatial stride of a 1x1 conv (the A map traverses W and H with this element stride); >= 1
   int early_weights;        // request the first stages' weight tiles before the grid dependency resolves (DC_EARLY_WEIGHTS)
+  float* sk_ws;             // split-K scratch: [unit][peer - 1][BN columns][128 rows] fp32 partial tiles (global memory, L2-resident)
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2 MMA with M = 256)
@@ -88,13 +89,12 @@ struct ConvCfg {
 
 // SK = 1 ("split-K", the latency regime: fewer work units than SMs): a cluster of S = 2 or 4 CTAs shares ONE unit,
 // CTA r accumulating K-steps [ksteps * r / S, ksteps * (r + 1) / S) into its own TMEM.  Each peer (r > 0) then adds
-// main + cross, writes the fp32 partial tile into its OWN (by then idle) pipeline stages and, once the leader has
-// signalled that its stages are idle too (remote mbarrier arrive), sends it with ONE bulk DSMEM copy
-// (cp.async.bulk.shared::cluster) into slot r - 1 of the leader's stage memory, completing on the leader's mbarrier;
-// the leader's epilogue sums own + slot 0 + slot 1 + ... in that fixed order (no atomics: repeated runs are bitwise
-// identical).  Scalar st.shared::cluster pushes and barrier.cluster syncs measured 6 us + 2 us per launch
-// (profiles/r1_microbench_latency.txt), more than the K loop they saved.  The grid is exactly units * S CTAs, so nothing
-// is persistent in this mode.
+// main + cross and writes the fp32 partial tile to a global scratch slot (it stays in L2: an SM moves ~64 B/clk to and
+// from L2 but only ~17 B/clk over distributed shared memory -- a version that exchanged the tiles by bulk DSMEM copies paid
+// ~7.5 us per launch, this one ~4.7 us, profiles/r1_microbench_latency.txt), fences, and arrives (release, cluster scope) on an
+// mbarrier in the leader's shared memory; the leader's epilogue waits on it (acquire, cluster scope), reads the slots
+// with L1-bypassing loads and sums own + slot 0 + slot 1 + ... in that fixed order (no atomics: repeated runs are bitwise
+// identical).  The grid is exactly units * S CTAs, so nothing is persistent in this mode.
 template <int BN, int CG, int EW, int SK = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -119,8 +119,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * kStages;
   uint64_t* tempty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  [[maybe_unused]] uint64_t* red_full = bars + 2 * kStages + 5;    // split-K leader: all peers' partial tiles have landed
-  [[maybe_unused]] uint64_t* peer_go = bars + 2 * kStages + 6;     // split-K peer: the leader's stage memory is idle
+  [[maybe_unused]] uint64_t* red_full = bars + 2 * kStages + 5;    // split-K leader: every peer has published its partial tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,8 +141,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tempty_bar[a], EW * CG);     // every epilogue warp of every CTA of the group
     }
     if (SK) {
-      mbar_init(red_full, 1);
-      mbar_init(peer_go, 1);
+      mbar_init(red_full, static_cast<uint32_t>(ksplit - 1));
     }
     fence_mbar_init();
   }
@@ -455,14 +453,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     if (p.out_mode == kOutSplitNHWC && p.res != nullptr && krank == 0) prefetch_residual(unit_first, half * 32);
     // split-K: fp32 partial tiles of the peers, slot s = CTA s + 1, [BN columns][128 rows] floats, in the stage memory
-    [[maybe_unused]] const float* slots = reinterpret_cast<const float*>(smem) + row;
+    [[maybe_unused]] const float* slots = p.sk_ws + static_cast<long long>(unit_first) * (ksplit - 1) * (BN * kBM) + row;
     [[maybe_unused]] auto add_partials = [&](uint32_t (&r)[32], uint32_t (&rx)[32], int c0) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(r[j]) + __uint_as_float(rx[j]);
-        for (int s_ = 0; s_ < ksplit - 1; ++s_) t += slots[(s_ * BN + c0 + j) * kBM];
-        r[j] = __float_as_uint(t);
+        r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rx[j]));
         rx[j] = 0u;
+      }
+      // one slot at a time, all 32 loads of a slot in flight together (they are L2 round trips: issued one by one
+      // behind their adds they cost ~19 us per launch, profiles/r1_microbench_latency.txt); rank order keeps the sum deterministic
+      for (int s_ = 0; s_ < ksplit - 1; ++s_) {
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = __ldcg(slots + (s_ * BN + c0 + j) * kBM);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + pv[j]);
       }
     };
     int acc = 0;
@@ -481,17 +486,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 2 * BN);
       if constexpr (SK != 0) {
-        static_assert(3 * BN * kBM * 4 <= Cfg::kStages * Cfg::kStageBytes, "three peer slots must fit the pipeline stages");
-        constexpr uint32_t kTileBytes = BN * kBM * 4;
-        // tfull observed: this CTA's MMAs -- the last readers of its pipeline stages -- are done, the stage memory is idle
         if (krank == 0) {
-          if (warp == 2 && lane == 0) {
-            mbar_expect_tx(red_full, static_cast<uint32_t>(ksplit - 1) * kTileBytes);
-            for (int r_ = 1; r_ < ksplit; ++r_) mbar_arrive_cluster(mapa_shared(smem_u32(peer_go), r_));
-          }
-          mbar_wait(red_full, 0);                      // the bulk copies' complete_tx: slots are visible to generic loads
+          mbar_wait_cluster(red_full, 0);              // every peer's tile is in L2 and visible
         } else {
-          float* mine = reinterpret_cast<float*>(smem) + row;
+          float* mine = p.sk_ws + (static_cast<long long>(unit) * (ksplit - 1) + (krank - 1)) * (BN * kBM) + row;
 #pragma unroll 1
           for (int c0 = half * 32; c0 < BN; c0 += 64) {
             uint32_t r[32], rx[32];
@@ -499,17 +497,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(taddr + BN + c0, rx);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mine[(c0 + j) * kBM] = __uint_as_float(r[j]) + __uint_as_float(rx[j]);
+            for (int j = 0; j < 32; ++j) __stcg(mine + (c0 + j) * kBM, __uint_as_float(r[j]) + __uint_as_float(rx[j]));   // 128 B per warp store
           }
-          fence_proxy_async_smem();                    // generic-proxy writes -> visible to the bulk-copy engine
-          named_bar_sync(1, EW * 32);                  // the whole tile is written (epilogue warps only)
+          // publish: the CTA barrier orders every epilogue thread's stores before the elected thread's gpu-scope release
+          // fence (cumulative), which the remote arrive (release, cluster scope) follows
+          named_bar_sync(1, EW * 32);
           if (warp == 2 && lane == 0) {
-            mbar_wait_cluster(peer_go, 0);
-            bulk_copy_to_cluster(mapa_shared(smem_u32(smem) + static_cast<uint32_t>(krank - 1) * kTileBytes, 0), smem, kTileBytes,
-                                 mapa_shared(smem_u32(red_full), 0));
+            fence_acq_rel_gpu();
+            mbar_arrive_cluster(mapa_shared(smem_u32(red_full), 0));
           }
-          continue;                                    // single unit per cluster: the peers are done (they stay resident
-        }                                              // until the final cluster barrier: the copy reads their smem)
+          continue;                                    // single unit per cluster: the peers are done
+        }
       }
       if (p.out_mode == kOutF32RowsT) {
         // swapped operands: row = weight row (output channel), columns = the tile's 128 pixels
@@ -673,7 +671,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  if (CG == 2 || SK) cluster_sync_all();       // nobody touches the peer's barriers / TMEM / shared memory after this
+  if (CG == 2) cluster_sync_all();             // nobody touches the peer's barriers / TMEM after this
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();

@@ -44,7 +44,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 // a layer's K loop is shared by a split-K cluster only from this many 64-channel K-steps on (DC_SPLIT_K_MIN_STEPS)
-std::atomic<int> g_split_k_min_steps{[] { const char* e = getenv("DC_SPLIT_K_MIN_STEPS"); const int v = e ? atoi(e) : 36; return v >= 8 ? v : 36; }()};
+std::atomic<int> g_split_k_min_steps{[] { const char* e = getenv("DC_SPLIT_K_MIN_STEPS"); const int v = e ? atoi(e) : 16; return v >= 8 ? v : 16; }()};
 bool g_inited = false;
 
 int ensure_init() {
@@ -253,6 +253,10 @@ int dc_set_split_k(int max_split) {
   return DC_OK;
 }
 int dc_get_split_k(void) { return g_split_k_max.load(); }
+size_t dc_splitk_workspace_bytes(void) {
+  // units * S <= SMs and a slot is at most a 128 x 128 fp32 tile: units * (S - 1) slots < SMs slots
+  return static_cast<size_t>(g_num_sms > 0 ? g_num_sms : 148) * 128 * 128 * 4;
+}
 int dc_set_split_k_min_steps(int min_ksteps) {
   if (min_ksteps < 8) return fail(DC_ERR_INVALID, "dc_set_split_k_min_steps: %d < 8 (every CTA of a 4-way split needs K-steps)", min_ksteps);
   g_split_k_min_steps.store(min_ksteps);
@@ -585,6 +589,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.out_mode = a->out_f32_rows == 2 ? dc::kOutF32RowsT : (a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC);
   p.swap_ab = a->out_f32_rows == 2;
   p.early_weights = use_early_weights();
+  p.sk_ws = static_cast<float*>(a->splitk_workspace);
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
@@ -600,16 +605,17 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   static const bool pair_lean_only = [] { const char* e = getenv("DC_CONV_PAIR_LEAN_ONLY"); return e && e[0] == '1'; }();
   static const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
   const bool lean_shape = lean_on && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res != nullptr && p.ntaps * p.Cin <= 512 && a->cout >= 256;
-  // Still fewer units than a quarter / half of the SMs and a K loop worth sharing (>= 16 K-steps: the exchange costs about
-  // as much as 4 of them, profiles/r1_microbench_latency.txt): split-K clusters of 4 / 2 CTAs per unit.  The summation order over K changes (S partial chains added in rank order), so results differ
+  // Still fewer units than a quarter / half of the SMs and a K loop worth sharing (>= 16 K-steps; the exchange costs ~4.7 us,
+  // a K-step ~0.4 us per CTA, profiles/r1_microbench_latency.txt): split-K clusters of 4 / 2 CTAs per unit.  The summation order over K changes (S partial chains added in rank order), so results differ
   // from the unsplit kernel by fp32 rounding; it is a pure function of the launch geometry, hence still deterministic.
   // dc_set_split_k(1) / DC_SPLIT_K=1 disables.
   int ksplit = 1;
-  if (p.out_mode != dc::kOutF32RowsT) {
+  if (p.out_mode != dc::kOutF32RowsT && a->splitk_workspace != nullptr) {
     const long long units = static_cast<long long>(p.n_tiles_m) * p.n_tiles_n;
     const int ksteps = p.ntaps * (a->cin / dc::kBK);
     for (int s = 4; s >= 2; s -= 2)
-      if (s <= g_split_k_max.load() && ksteps >= g_split_k_min_steps.load() && units <= (bn == 128 ? max_split_clusters<128>(s) : max_split_clusters<64>(s))) { ksplit = s; break; }
+      if (s <= g_split_k_max.load() && ksteps >= g_split_k_min_steps.load() && units <= (bn == 128 ? max_split_clusters<128>(s) : max_split_clusters<64>(s)) &&
+          static_cast<size_t>(units) * (s - 1) * bn * 128 * 4 <= a->splitk_workspace_bytes) { ksplit = s; break; }
   }
   const bool pair = ksplit == 1 && use_2cta() && !p.swap_ab && g_num_sms >= 2 && (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)));
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair ? bn / 2 : bn)) return rc;

@@ -11,7 +11,8 @@ class ConvArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int),
                 ("cout", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("pad", C.c_int), ("dilation", C.c_int),
                 ("w_packed", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
-                ("relu", C.c_int), ("out_f32_rows", C.c_int), ("ldc", C.c_int), ("out", C.c_void_p), ("stride", C.c_int)]
+                ("relu", C.c_int), ("out_f32_rows", C.c_int), ("ldc", C.c_int), ("out", C.c_void_p), ("stride", C.c_int),
+                ("splitk_workspace", C.c_void_p), ("splitk_workspace_bytes", C.c_size_t)]
 
 
 _SIGS = {
@@ -49,6 +50,7 @@ _SIGS = {
     "dc_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "dc_set_split_k": (C.c_int, [C.c_int]),
     "dc_get_split_k": (C.c_int, []),
+    "dc_splitk_workspace_bytes": (C.c_size_t, []),
     "dc_set_split_k_min_steps": (C.c_int, [C.c_int]),
     "dc_get_split_k_min_steps": (C.c_int, []),
     "dc_conv1_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -118,6 +118,10 @@ typedef struct dc_conv_args {
   int stride;                /* 0 or 1: unit stride.  > 1 (<= 8): 1x1 pad-0 convolutions with split output only; the A tensor map
                               * traverses W and H with this element stride, which is what im2col does for the reference's
                               * strided 1x1 convs (res3a/res4a branch1 + branch2a; im2col.cu:8-39) */
+  void* splitk_workspace;    /* NULL, or device scratch of >= dc_splitk_workspace_bytes() for the split-K clusters of under-filled
+                              * launches (see dc_set_split_k); without it such launches simply do not split.  No initialisation
+                              * needed; must not be shared by launches that can run concurrently (one per stream). */
+  size_t splitk_workspace_bytes;
 } dc_conv_args;
 /* Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-24) =
  * im2col_gpu (util/im2col.cu:8-62) + cublasSgemm (util/math_functions.cu:13-27) per image, and the
@@ -128,14 +132,17 @@ typedef struct dc_conv_args {
 int dc_conv_forward(const dc_conv_args* args, void* stream);
 /* Latency regime (one image; the reference's demo runs batch 1, python/pose/estimate_pose.py:224-243): when a layer has
  * fewer 128-pixel x N-channel work units than SMs, dc_conv_forward first halves the channel tile (bitwise-neutral) and
- * then shares each unit's K loop among a cluster of up to `max_split` CTAs (split-K, partial tiles reduced through
- * distributed shared memory in rank order: deterministic, but the fp32 summation order differs from the unsplit kernel).
+ * then, given args->splitk_workspace, shares each unit's K loop among a cluster of up to `max_split` CTAs (split-K; the
+ * partial tiles meet in the L2-resident workspace and are summed in rank order: deterministic, but the fp32 summation
+ * order differs from the unsplit kernel).
  * max_split in {1, 2, 4}; 1 = never split (bitwise batch-independent results at any size).  Default 4 (env DC_SPLIT_K).
  * Process-wide; takes effect for launches (and CUDA-graph captures) made after the call. */
 int dc_set_split_k(int max_split);
 int dc_get_split_k(void);
-/* A K loop is shared only from `min_ksteps` 64-channel K-steps on (taps * cin / 64; default 36 = a 3x3 convolution over 256
- * channels, env DC_SPLIT_K_MIN_STEPS): the exchange costs about as much as 8-15 K-steps (profiles/r1_microbench_latency.txt). */
+/* Upper bound of the scratch any split launch needs on this device (SM count x one 128 x 128 fp32 tile). */
+size_t dc_splitk_workspace_bytes(void);
+/* A K loop is shared only from `min_ksteps` 64-channel K-steps on (taps * cin / 64; env DC_SPLIT_K_MIN_STEPS): the exchange
+ * costs about as much as a few K-steps (profiles/r1_microbench_latency.txt). */
 int dc_set_split_k_min_steps(int min_ksteps);
 int dc_get_split_k_min_steps(void);
 

@@ -21,7 +21,7 @@ def init():
     libdc.check(libdc.lib().dc_init(torch.cuda.current_device()))
 
 
-def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_rows=False, stride=1):
+def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_rows=False, stride=1, split_k_workspace=True):
     """Runs dc_conv_forward on fp32 NCHW numpy inputs; returns fp32 NCHW numpy (or fp32 rows)."""
     L = libdc.lib()
     n, ci, h, wd = x_nchw.shape
@@ -41,10 +41,13 @@ def conv_bn(x_nchw, w, a, b, pad=0, dil=1, relu=True, residual_nchw=None, f32_ro
         out = torch.full((n * ho * wo, rows), float("nan"), dtype=torch.float32, device="cuda")
     else:
         out = torch.full((2, n, ho, wo, co), float("nan"), dtype=torch.float16, device="cuda")
+    ws_bytes = L.dc_splitk_workspace_bytes()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")       # split-K scratch (uninitialised on purpose)
     args = libdc.ConvArgs(x=xs.data_ptr(), n=n, h=h, w=wd, cin=ci, cout=co, kh=kh, kw=kw, pad=pad, dilation=dil,
                           w_packed=wp.data_ptr(), scale=sc.data_ptr(), shift=sh.data_ptr(),
                           residual=res.data_ptr() if res is not None else None, relu=int(relu),
-                          out_f32_rows=int(f32_rows), ldc=rows, out=out.data_ptr(), stride=stride)
+                          out_f32_rows=int(f32_rows), ldc=rows, out=out.data_ptr(), stride=stride,
+                          splitk_workspace=ws.data_ptr() if split_k_workspace else None, splitk_workspace_bytes=ws_bytes)
     libdc.check(L.dc_conv_forward(C.byref(args), stream_ptr()))
     torch.cuda.synchronize()
     if f32_rows:

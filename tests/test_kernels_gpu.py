@@ -108,7 +108,6 @@ def test_split_k_matches_oracle_and_unsplit_kernel(case, _gpu):
     ref = np.maximum(ref, 0)
     got = {}
     try:
-        libdc.check(L.dc_set_split_k_min_steps(16))      # default 36 (where splitting pays); 16 here so every case splits
         for s in (1, 2, 4):
             libdc.check(L.dc_set_split_k(s))
             got[s] = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True, residual_nchw=shortcut)
@@ -121,13 +120,12 @@ def test_split_k_matches_oracle_and_unsplit_kernel(case, _gpu):
         rows1 = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=False, f32_rows=True)
     finally:
         libdc.check(L.dc_set_split_k(4))
-        libdc.check(L.dc_set_split_k_min_steps(36))
     # the split only re-associates the fp32 sum over K
     for s in (2, 4):
         assert np.abs(got[s] - got[1]).max() < 5e-5, (s, np.abs(got[s] - got[1]).max())
     assert np.abs(rows[:, :co] - rows1[:, :co]).max() < 5e-5
     assert L.dc_set_split_k(3) != 0 and L.dc_get_split_k() == 4
-    assert L.dc_set_split_k_min_steps(4) != 0 and L.dc_get_split_k_min_steps() == 36
+    assert L.dc_set_split_k_min_steps(4) != 0 and L.dc_get_split_k_min_steps() == 16
 
 
 @pytest.mark.parametrize("co", [160, 192, 320])      # 320 >= 256 takes the 16-warp lean epilogue

@@ -69,9 +69,11 @@ def run_latency(n, h, w, cin, cout, k, pad, dil, residual, chain=50, reps=10):
     ho, wo = h + 2 * pad - (dil * (k - 1) + 1) + 1, w + 2 * pad - (dil * (k - 1) + 1) + 1
     res = torch.randn(2, n, ho, wo, cout, device="cuda").half() if residual else None
     out = torch.empty(2, n, ho, wo, cout, device="cuda", dtype=torch.half)
+    ws = torch.empty(L.dc_splitk_workspace_bytes(), dtype=torch.uint8, device="cuda")
     a = libdc.ConvArgs(x=x.data_ptr(), n=n, h=h, w=w, cin=cin, cout=cout, kh=k, kw=k, pad=pad, dilation=dil,
                        w_packed=wp.data_ptr(), scale=sc.data_ptr(), shift=sh.data_ptr(),
-                       residual=res.data_ptr() if residual else None, relu=1, out_f32_rows=0, ldc=0, out=out.data_ptr())
+                       residual=res.data_ptr() if residual else None, relu=1, out_f32_rows=0, ldc=0, out=out.data_ptr(),
+                       splitk_workspace=ws.data_ptr(), splitk_workspace_bytes=ws.numel())
     st = C.c_void_p()
     libdc.check(L.dc_stream_create(C.byref(st)))
     libdc.check(L.dc_conv_forward(C.byref(a), st))
@@ -93,8 +95,8 @@ def run_latency(n, h, w, cin, cout, k, pad, dil, residual, chain=50, reps=10):
     ms = C.c_float()
     libdc.check(L.dc_event_elapsed_ms(e0, e1, C.byref(ms)))
     L.dc_graph_destroy(g)
-    print("latency n%d %dx%d %d->%d k%d d%d res=%d split_k<=%d debug=%s : %.2f us / launch" %
-          (n, h, w, cin, cout, k, dil, residual, L.dc_get_split_k(), os.environ.get("DC_SK_DEBUG", "0"), ms.value * 1e3 / (chain * reps)))
+    print("latency n%d %dx%d %d->%d k%d d%d res=%d split_k<=%d from %d K-steps : %.2f us / launch" %
+          (n, h, w, cin, cout, k, dil, residual, L.dc_get_split_k(), L.dc_get_split_k_min_steps(), ms.value * 1e3 / (chain * reps)))
 
 
 if __name__ == "__main__":
