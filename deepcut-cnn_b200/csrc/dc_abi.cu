@@ -123,6 +123,7 @@ int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c,
   // traversal stride s: the box spans tw*s x th*s input pixels of which every s-th is loaded (tw x th rows of smem)
   const cuuint32_t box[5] = {(cuuint32_t)dc::kBK, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), 1, 1};
   const cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+  // L2 promotion 128 B = exactly the 64-channel row a K-step needs (256 B measured the same: 522 vs 522 images/s at 16x720p)
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -34,6 +34,22 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     assert L.dc_conv_forward(a, None) != 0
 
 
+def test_split_k_policy_setters_validate_their_arguments():
+    # host-side state only: no GPU needed
+    L = libdc.lib()
+    assert L.dc_get_split_k() == 4 and L.dc_get_split_k_min_steps() == 16          # defaults (env DC_SPLIT_K / DC_SPLIT_K_MIN_STEPS unset)
+    for bad in (0, 3, 8, -1):
+        assert L.dc_set_split_k(bad) != 0 and b"dc_set_split_k" in L.dc_last_error()
+    assert L.dc_set_split_k_min_steps(7) != 0
+    assert L.dc_set_split_k(2) == 0 and L.dc_get_split_k() == 2
+    assert L.dc_set_split_k_min_steps(36) == 0 and L.dc_get_split_k_min_steps() == 36
+    assert L.dc_set_split_k(4) == 0 and L.dc_set_split_k_min_steps(16) == 0
+    # one 128 x 128 fp32 tile per SM bounds any split launch's scratch
+    assert L.dc_splitk_workspace_bytes() >= 148 * 128 * 128 * 4
+    a = libdc.ConvArgs()
+    assert a.splitk_workspace is None and a.splitk_workspace_bytes == 0           # a zeroed struct never splits
+
+
 def test_pack_conv_weight_matches_numpy_split():
     rng = np.random.default_rng(0)
     for (co, ci, k) in ((64, 64, 1), (128, 64, 3), (14, 512, 1), (300, 64, 3)):
