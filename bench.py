@@ -299,6 +299,7 @@ def main():
         t = torch.tensor([ms.value, wall * 1e3], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed.window = (t0, t0 + wall)          # host-clock bounds of THIS rank's timed region (for the clock sampler)
         return float(t[0]), float(t[1])
 
     # ---- device-resident throughput
@@ -310,11 +311,9 @@ def main():
     for _ in range(max(args.warmup, 3) - 1):
         net.forward()
     launches0 = L.dc_launch_count()
-    t_region0 = time.time()
     dev_ms, wall_ms = timed(net.forward, args.steps)
-    t_region1 = time.time()
     launches = L.dc_launch_count() - launches0
-    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
+    clocks = sampler.stop(*timed.window) if rank == 0 else None
     value = world * B * args.steps / (dev_ms / 1e3)
 
     # ---- end to end through the Caffe API with host buffers
