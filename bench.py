@@ -34,6 +34,17 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "deepcut-cnn_b200", "python"))
 
 
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout under torchrun),
+# so file descriptor 1 is pointed at stderr for the life of the process and the line goes out through a private duplicate of
+# the original stdout.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,7 +237,7 @@ def run_reference(args, rank, world):
                        "images_per_step": per_step},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -254,8 +265,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout; stdout carries ONE JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
@@ -480,7 +489,7 @@ def main():
                         "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred", "mode": e2e_mode},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency,
                 "wall_ms_per_step": wall_ms / args.steps, "arena_mib": net.arena_bytes >> 20, "weights_mib": net.weight_bytes >> 20}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
