@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Minimal forward loop for ncu (never a bench number): builds the bench workload, runs --warm
-forwards, then --iters forwards.  One forward = 163 kernel launches at the default workload."""
+forwards, then --iters forwards.  One forward = 162 kernel launches at the default workload."""
 import argparse
 import importlib
 import os
