@@ -110,6 +110,12 @@ const float* caffe_blob_cpu_data(void* blob) { const float* p = nullptr; Guard([
 float* caffe_blob_mutable_cpu_diff(void* blob) { float* p = nullptr; Guard([&] { p = B(blob)->mutable_cpu_diff(); }); return p; }
 const float* caffe_blob_gpu_data(void* blob) { const float* p = nullptr; Guard([&] { p = B(blob)->gpu_data(); }); return p; }
 float* caffe_blob_mutable_gpu_data(void* blob) { float* p = nullptr; Guard([&] { p = B(blob)->mutable_gpu_data(); }); return p; }
+float* caffe_blob_overwrite_gpu_data(void* blob) { float* p = nullptr; Guard([&] { p = B(blob)->overwrite_gpu_data(); }); return p; }
+int caffe_blob_data_head(void* blob) {
+  int h = -1;
+  Guard([&] { CHECK(B(blob)->data()) << "blob has no memory yet"; h = static_cast<int>(B(blob)->data()->head()); });
+  return h;
+}
 
 int caffe_net_set_fusion(void* net, int on) { return Guard([&] { N(net)->set_fusion(on != 0); }); }
 int caffe_net_materialize_intermediates(void* net, int on) { return Guard([&] { N(net)->materialize_intermediates(on != 0); }); }

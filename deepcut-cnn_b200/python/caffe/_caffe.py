@@ -40,7 +40,7 @@ def _load():
         "caffe_blob_count": (ci, [vp]), "caffe_blob_reshape": (ci, [vp, ci, C.POINTER(ci)]),
         "caffe_blob_mutable_cpu_data": (vp, [vp]), "caffe_blob_cpu_data": (vp, [vp]),
         "caffe_blob_mutable_cpu_diff": (vp, [vp]), "caffe_blob_gpu_data": (vp, [vp]),
-        "caffe_blob_mutable_gpu_data": (vp, [vp]),
+        "caffe_blob_mutable_gpu_data": (vp, [vp]), "caffe_blob_overwrite_gpu_data": (vp, [vp]), "caffe_blob_data_head": (ci, [vp]),
         "caffe_net_set_fusion": (ci, [vp, ci]), "caffe_net_materialize_intermediates": (ci, [vp, ci]),
         "caffe_net_fused_last_forward": (ci, [vp]), "caffe_net_fusion_diagnostic": (cs, [vp]),
         "caffe_net_last_forward_launches": (C.c_longlong, [vp]),

@@ -71,6 +71,20 @@ class Blob(object):
         """Blob::mutable_gpu_data(): the device copy becomes the authoritative one (syncedmem.cpp:125-129)."""
         return check_ptr(lib.caffe_blob_mutable_gpu_data(self._h))
 
+    def cpu_data_ptr(self):
+        """Blob::cpu_data() (const): syncs a device-side head to the host, does NOT count as a host write."""
+        return check_ptr(lib.caffe_blob_cpu_data(self._h))
+
+    HEADS = ("UNINITIALIZED", "HEAD_AT_CPU", "HEAD_AT_GPU", "SYNCED")
+
+    @property
+    def data_head(self):
+        """SyncedMemory::head() of the data (include/caffe/syncedmem.hpp:65-66) as its enumerator's name."""
+        h = lib.caffe_blob_data_head(self._h)
+        if h < 0:
+            raise RuntimeError(last_error())
+        return self.HEADS[h]
+
 
 class _BlobArray(np.ndarray):
     """ndarray view that keeps its Blob (hence the C++ shared_ptr) alive."""

@@ -55,6 +55,11 @@ const float* caffe_blob_cpu_data(void* blob);
 float* caffe_blob_mutable_cpu_diff(void* blob);
 const float* caffe_blob_gpu_data(void* blob);
 float* caffe_blob_mutable_gpu_data(void* blob);
+float* caffe_blob_overwrite_gpu_data(void* blob);                      /* device pointer for a writer of every element: no upload first */
+/* SyncedMemory::head() of the blob's data (include/caffe/syncedmem.hpp:65-66): 0 UNINITIALIZED, 1 HEAD_AT_CPU, 2 HEAD_AT_GPU,
+ * 3 SYNCED; -1 + caffe_last_error() for a blob without memory.  Lets callers check the state machine the reference pins in
+ * src/caffe/test/test_syncedmem.cpp:16-125. */
+int caffe_blob_data_head(void* blob);
 
 /* B200 extensions */
 int caffe_net_set_fusion(void* net, int on);

@@ -121,6 +121,32 @@ def test_blob_memory_outlives_net(tmp_path):
     assert all(float(v.sum()) == 3.0 * v.size for v in views)
 
 
+def test_host_library_exports_every_symbol_its_header_declares():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "caffe_b200_c.h")).read()
+    declared = sorted(set(re.findall(r"\b(caffe_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) > 40
+    for name in declared:
+        assert hasattr(caffe._caffe.lib, name), "symbol %s declared in caffe_b200_c.h but not exported" % name
+    assert set(declared) == set(caffe._caffe.EXPORTS), sorted(set(declared) ^ set(caffe._caffe.EXPORTS))
+
+
+def test_syncedmem_head_host_side(tmp_path):
+    # SyncedMemoryTest.TestCPUWrite / TestInitialization (src/caffe/test/test_syncedmem.cpp:16-50), the transitions that need no
+    # device: a fresh blob's memory is UNINITIALIZED, the first host access allocates zeroed memory and moves the head to the CPU
+    path = dcutil.write_prototxt(tmp_path, stages=(1, 1, 1, 1), height=64, width=64)
+    net = caffe.Net(path, caffe.TEST)
+    b = net.blobs["prob"]
+    assert b.data_head == "UNINITIALIZED"
+    v = b.data
+    assert b.data_head == "HEAD_AT_CPU" and not v.any()              # lazily allocated, zero-initialised (syncedmem.cpp:25-33)
+    v[...] = 1.0
+    assert b.data_head == "HEAD_AT_CPU" and float(b.data.sum()) == v.size
+    b.reshape(1, 14, 4, 4)                                             # Reshape within capacity keeps the memory (blob.cpp:23-43)
+    assert b.data_head == "HEAD_AT_CPU" and float(b.data.sum()) == 14 * 16
+
+
 def test_errors_are_exceptions_not_aborts(tmp_path):
     with pytest.raises((IOError, OSError)):
         caffe.Net("/nonexistent/net.prototxt", caffe.TEST)

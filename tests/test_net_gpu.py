@@ -95,6 +95,44 @@ def test_reshape_and_repeat_is_bitwise_stable(tmp_path):
         assert np.array_equal(a[k], c[k]), k
 
 
+def test_syncedmem_head_state_machine(tmp_path):
+    """SyncedMemoryTest.TestGPURead / TestGPUWrite (src/caffe/test/test_syncedmem.cpp:52-125) through the Blob API: the 4-state head
+    and the copies each transition implies; plus the one extension, overwrite_gpu_data (no upload before a full overwrite)."""
+    import ctypes as C
+    caffe = dcutil.caffe_module()
+    L = dcutil.libdc.lib()
+    path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
+    net = netutil.product_net(path, weights)
+    b = net.blobs["data"]
+    b.reshape(1, 3, 64, 64)
+    nbytes = b.count * 4
+    v = b.data
+    v[...] = 1.0
+    assert b.data_head == "HEAD_AT_CPU"
+    gp = b.gpu_data_ptr()                              # const device access: upload, both copies valid
+    assert b.data_head == "SYNCED"
+    caffe.sync()                                       # the upload is stream-ordered on Caffe's stream; this test reads on stream 0
+    back = np.empty(b.count, np.float32)
+    dcutil.libdc.check(L.dc_memcpy_async(back.ctypes.data_as(C.c_void_p), C.c_void_p(gp), nbytes, 2, None))     # DC_D2H
+    dcutil.libdc.check(L.dc_device_sync())
+    assert np.all(back == 1.0)
+    assert b.cpu_data_ptr() and b.data_head == "SYNCED"          # const host access of a synced blob: nothing moves
+    b.data                                             # mutable host access: the host copy is authoritative again
+    assert b.data_head == "HEAD_AT_CPU"
+    mp = b.mutable_gpu_data_ptr()                      # mutable device access: re-upload (reference semantics), head at the GPU
+    assert b.data_head == "HEAD_AT_GPU" and mp == gp   # the allocation is reused
+    caffe.sync()
+    dcutil.libdc.check(L.dc_memset_async(C.c_void_p(mp), 0, nbytes, None))
+    dcutil.libdc.check(L.dc_device_sync())
+    assert b.cpu_data_ptr() and b.data_head == "SYNCED"          # const host access: download, both valid
+    assert not b.data.any()                            # ... and it really was downloaded (zeros now)
+    assert b.data_head == "HEAD_AT_CPU"
+    b.data[...] = 2.0
+    op = caffe._caffe.lib.caffe_blob_overwrite_gpu_data(b._h)   # extension: head to the GPU WITHOUT uploading the 2s
+    assert op == mp and b.data_head == "HEAD_AT_GPU"
+    assert not np.array(b.data).any()                  # the device copy (zeros) won: the host's 2s were not uploaded
+
+
 def test_host_weight_write_invalidates_packed_cache(tmp_path):
     path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
     net = netutil.product_net(path, weights)
