@@ -225,6 +225,27 @@ def test_full_depth_nets_match_oracle(tmp_path, stages, h, w, n):
     assert 0.01 < got["prob"].min() and got["prob"].max() < 0.99
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 107, 93), (3, 65, 130), (2, 33, 47), (1, 200, 17)])
+def test_ragged_input_sizes(tmp_path, n, h, w):
+    """Sizes that are no multiple of the net's strides: every stage has an odd, ragged map (107x93 -> conv1 54x47 -> ceil-mode
+    pool 27x24 -> 14x12 -> 7x6; the 2h+1 deconvolution output is cropped to the res3 map), tiles are partly outside the image at
+    every layer, and the batch of 3 mixes images in one tile grid.  200x17 is the narrowest the stem accepts gracefully (res5 is
+    13x2).  Checked against the reference's CPU code when its library is there, else the numpy oracle."""
+    path, weights = netutil.build(tmp_path, (1, 2, 2, 1), h, w)
+    x = dcutil.synth.images(n, h, w, seed=h * w)
+    if netutil.reference_available():
+        ref = netutil.reference_forward(path, weights, x, want=["prob", "loc_pred", "next_pred"])
+    else:
+        ref = netutil.oracle_forward(path, weights, x)
+    net = netutil.product_net(path, weights)
+    got = netutil.product_forward(net, x)
+    assert net.fused_last_forward, net.fusion_diagnostic
+    for k in ("prob", "loc_pred", "next_pred"):
+        assert got[k].shape == ref[k].shape, (k, got[k].shape, ref[k].shape)
+    errs = _report("ragged %dx%dx%d" % (n, h, w), got, ref)
+    assert max(errs.values()) < 1e-4
+
+
 @pytest.mark.parametrize("n,h,w", [(2, 64, 64), (1, 512, 512), (1, 720, 1280)])
 def test_resnet152_matches_the_reference_cpu_code(tmp_path, n, h, w):
     """The product against THE REFERENCE ITSELF (oracle/_ref: its CPU layer sources compiled from /root/reference,
