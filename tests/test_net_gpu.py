@@ -191,16 +191,17 @@ def test_batch_independence_and_determinism(tmp_path):
             assert netutil.max_err(one[k][0], split[k][i]) < 2e-5, (k, i)
 
 
-def test_full_size_tile_grid_properties(tmp_path):
+@pytest.mark.parametrize("h,w", [(720, 1280), (1080, 1920)])
+def test_full_size_tile_grid_properties(tmp_path, h, w):
     """BASELINE-size geometry (one 720p image: 90x160 output cells, ragged 45x80 res4/res5 maps) through the whole
     fused net: outputs finite, prob in (0, 1), and the top-left 256x256 crop's outputs agree with the full image's
     on the cells whose receptive field (< 16 cells of context here) lies inside the crop -- checks every kernel's edge
     handling at the real sizes without running the CPU oracle on 555 GFLOP."""
     path, weights = netutil.build(tmp_path, (1, 1, 1, 1), 64, 64)
     net = netutil.product_net(path, weights)
-    x = dcutil.synth.images(1, 720, 1280, seed=6)
+    x = dcutil.synth.images(1, h, w, seed=6)
     big = netutil.product_forward(net, x)
-    assert big["prob"].shape == (1, 14, 90, 160) and big["next_pred"].shape == (1, 364, 90, 160)
+    assert big["prob"].shape == (1, 14, h // 8, w // 8) and big["next_pred"].shape == (1, 364, h // 8, w // 8)
     for k in big:
         assert np.isfinite(big[k]).all(), k
     assert big["prob"].min() > 0 and big["prob"].max() < 1
@@ -225,12 +226,13 @@ def test_full_depth_nets_match_oracle(tmp_path, stages, h, w, n):
     assert 0.01 < got["prob"].min() and got["prob"].max() < 0.99
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 107, 93), (3, 65, 130), (2, 33, 47), (1, 200, 17)])
+@pytest.mark.parametrize("n,h,w", [(1, 107, 93), (3, 65, 130), (2, 33, 47), (1, 200, 17), (1, 16, 16), (2, 8, 8), (1, 9, 40), (40, 32, 32)])
 def test_ragged_input_sizes(tmp_path, n, h, w):
     """Sizes that are no multiple of the net's strides: every stage has an odd, ragged map (107x93 -> conv1 54x47 -> ceil-mode
     pool 27x24 -> 14x12 -> 7x6; the 2h+1 deconvolution output is cropped to the res3 map), tiles are partly outside the image at
-    every layer, and the batch of 3 mixes images in one tile grid.  200x17 is the narrowest the stem accepts gracefully (res5 is
-    13x2).  Checked against the reference's CPU code when its library is there, else the numpy oracle."""
+    every layer, and the batch of 3 mixes images in one tile grid; 200x17: res5 is 13x2.  Minimum sizes: 8x8 -> every map from
+    res3 on is ONE pixel (1x1 output cells; TMA boxes far larger than the tensors); 40 images of 32x32: more images than pixels
+    per tile.  Checked against the reference's CPU code when its library is there, else the numpy oracle."""
     path, weights = netutil.build(tmp_path, (1, 2, 2, 1), h, w)
     x = dcutil.synth.images(n, h, w, seed=h * w)
     if netutil.reference_available():
