@@ -108,6 +108,32 @@ def test_max_pool_literal_matrices():
     assert np.array_equal(y[0, 0], np.array([[14, 16, 17], [26, 28, 29], [32, 34, 35]], np.float32))
     # padded case shape rule (test_pooling_layer.cpp:478-521 geometry: 3x3 pad 1 stride 2 on 3x3 -> 2x2)
     assert R.pool_out_size(3, 3, 1, 2) == 2
+    # PoolingLayerTest.TestForwardMaxPadded (test_pooling_layer.cpp:478-521): 3x3 / stride 2 / pad 2 over
+    # [1 2 4; 2 3 2; 4 2 1] -> 3x3 [1 4 4; 4 4 4; 4 4 1] (windows clipped to the image, exact)
+    x = np.array([[1, 2, 4], [2, 3, 2], [4, 2, 1]], np.float32).reshape(1, 1, 3, 3)
+    y = R.max_pool(x, 3, 2, pad=2)
+    assert y.shape == (1, 1, 3, 3)
+    assert np.array_equal(y[0, 0], np.array([[1, 4, 4], [4, 4, 4], [4, 4, 1]], np.float32))
+
+
+def test_gemv_known_answers_and_bias_broadcast():
+    # GemmTest.TestGemvCPUGPU (test_util_blas.cpp:89-130): A = [1 2 3; 4 5 6], A x = [14 32], A^T [1 2] = [9 12 15] -- the
+    # K = 1 / N = 1 GEMMs the reference's bias path is made of (base_conv_layer.cpp:274-280), exact integers
+    A = np.array([[1, 2, 3], [4, 5, 6]], np.float32)
+    assert np.array_equal(R.sgemm(A, np.array([[1], [2], [3]], np.float32))[:, 0], np.array([14, 32], np.float32))
+    assert np.array_equal(R.sgemm(A.T.copy(), np.array([[1], [2]], np.float32))[:, 0], np.array([9, 12, 15], np.float32))
+    # forward_cpu_bias: Y += bias * ones^T as a K = 1 GEMM == a per-channel broadcast add
+    # (BiasLayerTest.TestForwardBroadcastMiddle, test_bias_layer.cpp:199-316: y = x + b broadcast over axis 1), 1e-5
+    rng = np.random.default_rng(99)
+    x = rng.standard_normal((2, 3, 4, 5)).astype(np.float32)
+    b = rng.standard_normal(3).astype(np.float32)
+    y = R.scale_bias(x, np.ones(3, np.float32), b)
+    for c in range(3):
+        assert np.abs(y[:, c] - (x[:, c] + b[c])).max() < 1e-5
+    w = rng.standard_normal((3, 3, 1, 1)).astype(np.float32)
+    yc = R.convolution(x, w, b, 1, 0, 1)                      # the head layers' bias term through the conv path itself
+    ref = np.einsum("oi,nihw->nohw", w[:, :, 0, 0].astype(np.float64), x.astype(np.float64)) + b.reshape(1, 3, 1, 1)
+    assert np.abs(yc - ref).max() < 1e-5
 
 
 def test_scale_bias_eltwise_relu_sigmoid_properties():
