@@ -108,6 +108,104 @@ def test_caffemodel_round_trip(tmp_path):
     assert b"\xa2\x06" in raw[:64] and len(raw) > 4 * sum(b.count for bl in net.params.values() for b in bl)
 
 
+def _caffe_subset_messages(packed=True):
+    """NetParameter / LayerParameter / BlobProto / BlobShape with the reference's field numbers (src/caffe/proto/caffe.proto:6-22,
+    64-100, 310-330), built at run time for the installed google.protobuf: the bytes below are written by the real protobuf
+    library, not by this repo's own wire-format writer."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    pkg = "caffe_subset_%s" % ("packed" if packed else "unpacked")
+    fd = descriptor_pb2.FileDescriptorProto(name=pkg + ".proto", package=pkg, syntax="proto2")
+
+    def msg(name):
+        m = fd.message_type.add()
+        m.name = name
+        return m
+
+    def field(m, name, num, typ, label=F.LABEL_OPTIONAL, type_name=None, pack=False):
+        f = m.field.add()
+        f.name, f.number, f.type, f.label = name, num, typ, label
+        if type_name:
+            f.type_name = "." + pkg + "." + type_name
+        if label == F.LABEL_REPEATED and typ in (F.TYPE_FLOAT, F.TYPE_DOUBLE, F.TYPE_INT64):
+            f.options.packed = pack
+    bs = msg("BlobShape")
+    field(bs, "dim", 1, F.TYPE_INT64, F.LABEL_REPEATED, pack=packed)
+    bp = msg("BlobProto")
+    field(bp, "shape", 7, F.TYPE_MESSAGE, type_name="BlobShape")
+    field(bp, "data", 5, F.TYPE_FLOAT, F.LABEL_REPEATED, pack=packed)
+    field(bp, "double_data", 8, F.TYPE_DOUBLE, F.LABEL_REPEATED, pack=packed)
+    for n, i in (("num", 1), ("channels", 2), ("height", 3), ("width", 4)):
+        field(bp, n, i, F.TYPE_INT32)
+    lp = msg("LayerParameter")
+    field(lp, "name", 1, F.TYPE_STRING)
+    field(lp, "type", 2, F.TYPE_STRING)
+    field(lp, "bottom", 3, F.TYPE_STRING, F.LABEL_REPEATED)
+    field(lp, "top", 4, F.TYPE_STRING, F.LABEL_REPEATED)
+    field(lp, "blobs", 7, F.TYPE_MESSAGE, F.LABEL_REPEATED, type_name="BlobProto")
+    field(lp, "from_the_future", 9999, F.TYPE_STRING)         # a field this reader has never heard of: must be skipped
+    field(lp, "future_number", 9998, F.TYPE_FIXED64)
+    npm = msg("NetParameter")
+    field(npm, "name", 1, F.TYPE_STRING)
+    field(npm, "layer", 100, F.TYPE_MESSAGE, F.LABEL_REPEATED, type_name="LayerParameter")
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName(pkg + ".NetParameter"))
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_caffemodel_written_by_real_protobuf(tmp_path, packed):
+    """Net::CopyTrainedLayersFrom (net.cpp:805-858) on a .caffemodel serialised by google.protobuf itself, in every blob encoding the
+    reference's Blob::FromProto accepts (blob.cpp:420-470): `shape` + packed float `data`; the deprecated 4-D num/channels/height/
+    width header; `double_data`; unpacked repeated scalars (a proto2 parser must take both); unknown fields are skipped; a layer
+    the net does not have is ignored."""
+    pytest.importorskip("google.protobuf")
+    NetMsg = _caffe_subset_messages(packed)
+    path = dcutil.write_prototxt(tmp_path, stages=(1, 1, 1, 1), height=64, width=64)
+    net = caffe.Net(path, caffe.TEST)
+    rng = np.random.default_rng(5)
+    want = {}
+    m = NetMsg(name="written by protobuf")
+    stranger = m.layer.add(name="not_in_this_net", type="Convolution")
+    stranger.blobs.add().data.extend([1.0, 2.0])
+    for li, (name, blobs) in enumerate(net.params.items()):
+        layer = m.layer.add(name=name, type="whatever")
+        layer.from_the_future = "x" * 300
+        layer.future_number = 7
+        want[name] = []
+        for b in blobs:
+            a = rng.standard_normal(b.shape).astype(np.float32)
+            want[name].append(a)
+            pb = layer.blobs.add()
+            style = li % 3
+            if style == 1 and a.ndim <= 4:            # deprecated 4-D header, missing leading axes are 1
+                dims = [1] * (4 - a.ndim) + list(a.shape)
+                pb.num, pb.channels, pb.height, pb.width = dims
+            else:
+                pb.shape.dim.extend(a.shape)
+            if style == 2:
+                pb.double_data.extend(a.astype(np.float64).ravel().tolist())
+            else:
+                pb.data.extend(a.ravel().tolist())
+    model = os.path.join(str(tmp_path), "protobuf_%d.caffemodel" % packed)
+    open(model, "wb").write(m.SerializeToString())
+    net.copy_from(model)
+    for name, arrays in want.items():
+        for a, b in zip(arrays, net.params[name]):
+            assert np.array_equal(a, b.data), name
+    # and the files this repo writes parse back with the real library, bit for bit
+    ours = os.path.join(str(tmp_path), "ours.caffemodel")
+    net.save(ours)
+    back = NetMsg()
+    back.ParseFromString(open(ours, "rb").read())
+    got = {l.name: l for l in back.layer}
+    for name, arrays in want.items():
+        assert name in got and len(got[name].blobs) == len(arrays)
+        for a, pb in zip(arrays, got[name].blobs):
+            assert list(pb.shape.dim) == list(a.shape)
+            assert np.array_equal(np.array(pb.data, np.float32).reshape(a.shape), a)
+
+
 def test_blob_memory_outlives_net(tmp_path):
     # python/caffe/test/test_net.py:48-60
     path = dcutil.write_prototxt(tmp_path, stages=(1, 1, 1, 1), height=64, width=64)
