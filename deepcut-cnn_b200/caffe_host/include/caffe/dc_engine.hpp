@@ -42,7 +42,9 @@ class PlanWeightCache {
 
 class FusedPlan {
  public:
-  static FusedPlan* Build(Net<float>& net, bool materialize, std::string* why_not, std::shared_ptr<PlanWeightCache>* cache);
+  // dry_run: match, schedule and place the arena WITHOUT touching the device (no allocation, no weight upload): what
+  // caffe_net_describe_plan and the CPU tests of the planner use.  A dry-run plan cannot Run().
+  static FusedPlan* Build(Net<float>& net, bool materialize, std::string* why_not, std::shared_ptr<PlanWeightCache>* cache, bool dry_run = false);
   ~FusedPlan();
   void Run();
   // true when a parameter blob was written on the host since the weights were packed
@@ -60,11 +62,21 @@ class FusedPlan {
 
   struct Tensor;
   struct Step;
+  // One launch group of the schedule: step `step` over images [i0, i0 + cn) of its tensors (cn = 0: the whole batch).
+  struct Issue { int step, i0, cn; };
+  // A run of consecutive ConvBN steps (the bottleneck blocks of one ResNet stage) executed sub-batch by sub-batch so that
+  // the block intermediates stay in L2 (PlanSchedule); chunk = images per pass.
+  struct Segment { int first, last, chunk; size_t bytes_per_image; };
+  const std::vector<Segment>& segments() const { return segments_; }
 
  private:
   FusedPlan() {}
   bool Match(Net<float>& net, bool materialize, std::string* why);
-  void PlanMemory();
+  void PlanSchedule();
+  void PlanMemory(bool dry_run);
+  // Replays the schedule against the arena placement on the host: every (tensor, image) a launch reads must still be owned by
+  // that tensor's last writer -- catches liveness / aliasing / chunk-order mistakes of the planner.  Empty string = consistent.
+  std::string VerifySchedule() const;
   void UploadWeights(Net<float>& net);
 
   Net<float>* net_ = nullptr;
@@ -83,7 +95,9 @@ class FusedPlan {
   std::vector<const void*> graph_ptrs_;
   bool graph_failed_ = false;
   void IssueSteps(const std::vector<const void*>& blob_ptrs, void* stream);
-  std::vector<void*> events_;
+  std::vector<void*> events_;          // step timing: one event before every Issue + one at the end
+  std::vector<Issue> schedule_;
+  std::vector<Segment> segments_;
 };
 
 }  // namespace caffe

@@ -3,6 +3,7 @@
 // binding is ctypes over these functions).  Every call catches the host's CHECK failures
 // (caffe::FatalError) and turns them into a non-zero return + caffe_last_error().
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "caffe/caffe.hpp"
@@ -141,6 +142,17 @@ int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, doubl
 }
 long long caffe_net_arena_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->arena_bytes() : 0; }
 long long caffe_net_weight_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->weight_bytes() : 0; }
+int caffe_net_describe_plan(void* net, char* out, int out_cap) {
+  return Guard([&] {
+    N(net)->Reshape();
+    std::string why;
+    std::unique_ptr<FusedPlan> plan(FusedPlan::Build(*N(net), false, &why, nullptr, /*dry_run=*/true));
+    CHECK(plan) << "the net does not fuse: " << why;
+    const std::string s = plan->Describe();
+    CHECK_LT((int)s.size(), out_cap) << "output buffer too small";
+    memcpy(out, s.c_str(), s.size() + 1);
+  });
+}
 
 int caffe_insert_splits_text(const char* prototxt_text, char* out, int out_cap) {
   return Guard([&] {

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <iterator>
 #include <map>
 #include <sstream>
 
@@ -25,6 +27,9 @@ struct FusedPlan::Tensor {
   int producer_layer = -1;            // -1: net input
   std::vector<int> consumers;         // layer ids reading it (Split layers excluded)
   int def_step = -1, last_step = -1;  // liveness in step indices
+  int alloc_step = -1, free_step = -1;  // arena residency (liveness widened to whole segments for tensors crossing a chunked one)
+  int chunk_n = 0;                    // > 0: lives entirely inside a chunked segment; the arena holds this many images of it
+  bool gave_memory = false;           // its storage was taken over in place by the step that read it last (block output over shortcut)
   size_t bytes = 0, offset = 0;       // arena placement
   void* ptr = nullptr;                // resolved device address (arena tensors)
   size_t elems() const { return static_cast<size_t>(n) * c * h * w; }
@@ -412,9 +417,9 @@ void PlanWeightCache::Snapshot(Net<float>& net) {
     }
 }
 
-FusedPlan* FusedPlan::Build(Net<float>& net, bool materialize, std::string* why_not, std::shared_ptr<PlanWeightCache>* cache) {
+FusedPlan* FusedPlan::Build(Net<float>& net, bool materialize, std::string* why_not, std::shared_ptr<PlanWeightCache>* cache, bool dry_run) {
   FusedPlan* plan = new FusedPlan();
-  if (cache && *cache && !(*cache)->Stale()) plan->weights_ = *cache;
+  if (!dry_run && cache && *cache && !(*cache)->Stale()) plan->weights_ = *cache;
   plan->net_ = &net;
   plan->materialize_ = materialize;
   std::string why;
@@ -424,7 +429,11 @@ FusedPlan* FusedPlan::Build(Net<float>& net, bool materialize, std::string* why_
     return nullptr;
   }
   if (why_not) why_not->clear();
-  plan->PlanMemory();
+  plan->PlanSchedule();
+  plan->PlanMemory(dry_run);
+  const std::string bad = plan->VerifySchedule();
+  if (!bad.empty()) LOG(FATAL) << "fused plan: inconsistent schedule: " << bad;
+  if (dry_run) return plan;
   plan->UploadWeights(net);
   if (cache) *cache = plan->weights_;
   return plan;
@@ -456,19 +465,134 @@ bool FusedPlan::Match(Net<float>& net, bool materialize, std::string* why) {
   return true;
 }
 
-// Liveness-based placement of every arena tensor (first-fit over a sorted free list).
-void FusedPlan::PlanMemory() {
-  for (size_t s = 0; s < steps_.size(); ++s) {
+namespace {
+size_t EnvMiB(const char* name, size_t dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? static_cast<size_t>(atof(e) * 1048576.0) : dflt;
+}
+bool EnvOn(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? e[0] != '0' : dflt;
+}
+}  // namespace
+
+// Step-order liveness, then the L2-resident schedule: the steps are grouped into SEGMENTS -- the bottleneck blocks of one
+// ResNet stage, i.e. consecutive ConvBN steps whose block outputs share one geometry -- and a segment whose per-image working
+// set (the block input/shortcut, which the block output overwrites in place, plus the two narrow intermediates) fits the L2
+// budget several times over is executed sub-batch by sub-batch: all its steps for images [0, c), then for [c, 2c), ...  Within
+// a pass every activation a conv reads was written a few launches earlier by the same pass and is still in the 126 MB L2, and
+// the tensors that never leave the segment are allocated for c images only, so successive passes overwrite the same lines
+// instead of streaming 16 images' worth of each tensor through HBM (75 GB per-conv vs 33 GB block-fused).
+// DC_L2_CHUNK_MB sets the budget (0 = off); DC_CHUNK_PLAN="c0,c1,.." forces the images per pass of the candidate segments in order.
+void FusedPlan::PlanSchedule() {
+  const int ns = static_cast<int>(steps_.size());
+  for (int s = 0; s < ns; ++s) {
     Step* st = steps_[s];
-    if (st->ws) { st->ws->def_step = static_cast<int>(s); st->ws->last_step = static_cast<int>(s); }
+    if (st->ws) { st->ws->def_step = s; st->ws->last_step = s; }
     Tensor* ins[3] = {st->in, st->in2, st->col};
     for (Tensor* t : ins)
-      if (t) t->last_step = std::max(t->last_step, static_cast<int>(s));
+      if (t) t->last_step = std::max(t->last_step, s);
     if (st->out && st->out->def_step < 0) {
-      st->out->def_step = static_cast<int>(s);
-      st->out->last_step = std::max(st->out->last_step, static_cast<int>(s));
+      st->out->def_step = s;
+      st->out->last_step = std::max(st->out->last_step, s);
     }
   }
+  for (Tensor* t : tensors_) { t->alloc_step = t->def_step; t->free_step = t->last_step; }
+
+  const size_t budget = EnvMiB("DC_L2_CHUNK_MB", 80u << 20);
+  std::vector<int> forced;
+  if (const char* e = getenv("DC_CHUNK_PLAN")) {
+    std::stringstream ss(e);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) forced.push_back(atoi(tok.c_str()));
+  }
+  const bool inplace = EnvOn("DC_INPLACE_RESIDUAL", true);
+  auto chunkable = [&](const Step* st) {
+    return st->type == Step::kConvBN && st->in->kind == Tensor::kSplit && st->out->kind == Tensor::kSplit && st->in->n > 1 &&
+           st->out->n == st->in->n && (!st->in2 || (st->in2->kind == Tensor::kSplit && st->in2->n == st->in->n));
+  };
+  size_t candidate = 0;
+  auto close_segment = [&](int a, int b) {
+    if (b <= a) return;
+    const int N = steps_[a]->in->n;
+    auto local = [&](const Tensor* t) { return t && t->bytes == 0 && t->kind == Tensor::kSplit && t->def_step >= a && t->last_step <= b; };
+    // per-image working set: the largest sum of segment-local tensors alive at one step (a block output that takes over its
+    // shortcut's storage counts once)
+    size_t ws = 0;
+    for (int j = a; j <= b; ++j) {
+      size_t live = 0;
+      for (const Tensor* t : tensors_)
+        if (local(t) && t->def_step <= j && j <= t->last_step) live += t->elems() / N * 4;
+      const Step* st = steps_[j];
+      if (inplace && st->in2 && local(st->in2) && local(st->out) && st->in2->last_step == j && st->in2 != st->in && st->in2->elems() == st->out->elems())
+        live -= st->out->elems() / N * 4;
+      ws = std::max(ws, live);
+    }
+    int chunk = N;
+    if (candidate < forced.size()) chunk = forced[candidate] > 0 ? std::min(forced[candidate], N) : N;
+    else if (budget > 0 && ws > 0 && ws <= budget) chunk = static_cast<int>(std::min<size_t>(N, budget / ws));
+    ++candidate;
+    if (chunk < N) {                       // even passes: 16 images at 5 per pass -> 4 passes of 4
+      const int passes = (N + chunk - 1) / chunk;
+      chunk = (N + passes - 1) / passes;
+    }
+    Segment seg = {a, b, chunk, ws};
+    segments_.push_back(seg);
+    if (chunk >= N) return;
+    // DC_PLAN_BREAK_LIVENESS=1 (tests only) leaves out the widening below, which VerifySchedule must then reject
+    const bool widen = !EnvOn("DC_PLAN_BREAK_LIVENESS", false);
+    for (Tensor* t : tensors_) {
+      if (local(t)) { t->chunk_n = chunk; continue; }
+      if (t->def_step < 0 || !widen) continue;
+      // a tensor that crosses the segment boundary must own its storage for the WHOLE segment: pass k+1 still reads the
+      // segment inputs after pass k has written the segment outputs
+      if (t->def_step < a && t->last_step >= a && t->last_step <= b) t->free_step = std::max(t->free_step, b);
+      if (t->def_step >= a && t->def_step <= b && t->last_step > b) t->alloc_step = std::min(t->alloc_step, a);
+    }
+  };
+  for (int s = 0; s < ns;) {
+    if (!chunkable(steps_[s])) { ++s; continue; }
+    int e = s;
+    while (e + 1 < ns && chunkable(steps_[e + 1]) && steps_[e + 1]->in->n == steps_[s]->in->n) ++e;
+    // blocks end at the convs that absorb a shortcut; consecutive blocks with the same output geometry form a segment
+    int seg_first = s, block_first = s;
+    long long key = -1;
+    for (int j = s; j <= e; ++j) {
+      if (!steps_[j]->in2) continue;
+      const Tensor* o = steps_[j]->out;
+      const long long k = (static_cast<long long>(o->h) * 65536 + o->w) * 65536 + o->c;
+      if (key >= 0 && k != key) { close_segment(seg_first, block_first - 1); seg_first = block_first; }
+      key = k;
+      block_first = j + 1;
+    }
+    close_segment(seg_first, e);
+    s = e + 1;
+  }
+  // the launch order
+  std::vector<int> seg_of(ns, -1);
+  for (size_t g = 0; g < segments_.size(); ++g)
+    for (int j = segments_[g].first; j <= segments_[g].last; ++j) seg_of[j] = static_cast<int>(g);
+  for (int s = 0; s < ns;) {
+    const int g = seg_of[s];
+    if (g < 0 || segments_[g].chunk >= steps_[s]->in->n) {
+      Issue is = {s, 0, 0};
+      schedule_.push_back(is);
+      ++s;
+      continue;
+    }
+    const Segment& seg = segments_[g];
+    const int N = steps_[s]->in->n;
+    for (int i0 = 0; i0 < N; i0 += seg.chunk)
+      for (int j = seg.first; j <= seg.last; ++j) {
+        Issue is = {j, i0, std::min(seg.chunk, N - i0)};
+        schedule_.push_back(is);
+      }
+    s = seg.last + 1;
+  }
+}
+
+// Liveness-based placement of every arena tensor (first-fit over a sorted free list).
+void FusedPlan::PlanMemory(bool dry_run) {
   struct Free { size_t off, size; };
   std::vector<Free> free_list;
   size_t top = 0;
@@ -509,28 +633,118 @@ void FusedPlan::PlanMemory() {
       free_list.erase(free_list.begin() + i);
     }
   };
+  auto size_of = [](const Tensor* t) -> size_t {
+    if (t->kind == Tensor::kRaw) return t->raw_bytes;
+    if (t->kind == Tensor::kF32Rows) return static_cast<size_t>(t->n) * t->h * t->w * t->ld * 4;
+    if (t->kind != Tensor::kSplit) return 0;
+    return t->chunk_n > 0 ? t->elems() / t->n * t->chunk_n * 4 : t->elems() * 4;
+  };
+  const bool inplace = EnvOn("DC_INPLACE_RESIDUAL", true);
   for (size_t s = 0; s < steps_.size(); ++s) {
-    if (Tensor* w = steps_[s]->ws) {
-      w->bytes = w->raw_bytes;
-      w->offset = alloc(w->bytes);
+    const int si = static_cast<int>(s);
+    // In place: a block's output takes over the storage of the shortcut it absorbs when this step is the shortcut's last
+    // reader (every element is read, then written, by the same epilogue warp; the conv's own input is another tensor).
+    // Halves the block's resident footprint and turns the output's write misses into hits on lines the read just brought in.
+    Step* st = steps_[s];
+    Tensor* taken = nullptr;
+    if (inplace && st->type == Step::kConvBN && st->in2 && st->out && st->in2 != st->in && st->in2->bytes && !st->in2->gave_memory &&
+        st->in2->free_step == si && st->out->alloc_step == si && st->out->bytes == 0 && size_of(st->out) == st->in2->bytes &&
+        st->in2->chunk_n == st->out->chunk_n) {
+      taken = st->in2;
+      st->out->bytes = taken->bytes;
+      st->out->offset = taken->offset;
+      taken->gave_memory = true;
     }
-    Tensor* t = steps_[s]->out;
-    if (t && t->def_step == static_cast<int>(s) && (t->kind == Tensor::kSplit || t->kind == Tensor::kF32Rows)) {
-      t->bytes = t->kind == Tensor::kSplit ? t->elems() * 4 : static_cast<size_t>(t->n) * t->h * t->w * t->ld * 4;
-      t->offset = alloc(t->bytes);
+    for (Tensor* t : tensors_) {
+      if (t->alloc_step != si || t->bytes) continue;
+      const size_t b = size_of(t);
+      if (!b) continue;
+      t->bytes = b;
+      t->offset = alloc(b);
     }
     for (Tensor* u : tensors_)
-      if (u->bytes && u->last_step == static_cast<int>(s)) release(u->offset, u->bytes);
+      if (u->bytes && u->free_step == si && !u->gave_memory) release(u->offset, u->bytes);
   }
   // the tail of the arena is the split-K scratch of this plan's under-filled conv launches (dc_conv_args.splitk_workspace):
   // one region for the whole plan, the launches that use it are serialised on the plan's stream
   splitk_ws_bytes_ = dc_splitk_workspace_bytes();
   const size_t ws_off = AlignUp(std::max<size_t>(top, 1024), 1024);
   arena_bytes_ = ws_off + splitk_ws_bytes_;
+  if (dry_run) return;
   DC_CHECK(dc_malloc(&arena_, arena_bytes_));
   splitk_ws_ = static_cast<char*>(arena_) + ws_off;
   for (Tensor* t : tensors_)
     if (t->bytes) t->ptr = static_cast<char*>(arena_) + t->offset;
+}
+
+std::string FusedPlan::VerifySchedule() const {
+  // ownership of arena bytes: interval start -> (end, tensor id, image or -1 for an unsliced tensor)
+  struct Own { size_t end; int tensor, image; };
+  std::map<size_t, Own> own;
+  auto write = [&](size_t b, size_t e, int tensor, int image) {
+    if (b >= e) return;
+    auto it = own.lower_bound(b);
+    if (it != own.begin()) {
+      auto pr = std::prev(it);
+      if (pr->second.end > b) {                       // split the interval that straddles b
+        Own tail = pr->second;
+        pr->second.end = b;
+        if (tail.end > e) own[e] = tail;
+      }
+    }
+    it = own.lower_bound(b);
+    while (it != own.end() && it->first < e) {
+      if (it->second.end > e) { Own tail = it->second; own.erase(it); own[e] = tail; break; }
+      it = own.erase(it);
+    }
+    Own o = {e, tensor, image};
+    own[b] = o;
+  };
+  auto owned = [&](size_t b, size_t e, int tensor, int image) {
+    size_t pos = b;
+    auto it = own.upper_bound(b);
+    if (it != own.begin()) --it;
+    for (; it != own.end() && pos < e; ++it) {
+      if (it->second.end <= pos) continue;
+      if (it->first > pos || it->second.tensor != tensor || it->second.image != image) return false;
+      pos = it->second.end;
+    }
+    return pos >= e;
+  };
+  // visits the arena ranges of images [i0, i0 + cn) of tensor t (both planes of a split tensor)
+  auto ranges = [&](const Tensor* t, int i0, int cn, const std::function<bool(size_t, size_t, int)>& fn) {
+    if (!t || !t->bytes) return true;
+    if (t->kind != Tensor::kSplit) return fn(t->offset, t->offset + t->bytes, -1);
+    const size_t img = t->elems() / t->n * 2;
+    const int first = cn > 0 ? i0 : 0, count = cn > 0 ? cn : t->n;
+    const bool local = t->chunk_n > 0;
+    if (local && (cn == 0 || cn > t->chunk_n)) return false;
+    const size_t plane = local ? static_cast<size_t>(count) * img : static_cast<size_t>(t->n) * img;
+    for (int k = 0; k < count; ++k) {
+      const size_t slot = local ? k : first + k;
+      if (!fn(t->offset + slot * img, t->offset + (slot + 1) * img, first + k)) return false;
+      if (!fn(t->offset + plane + slot * img, t->offset + plane + (slot + 1) * img, first + k)) return false;
+    }
+    return true;
+  };
+  for (const Issue& is : schedule_) {
+    const Step* st = steps_[is.step];
+    const Tensor* reads[3] = {st->in, st->type == Step::kConvBN || st->type == Step::kHeadFinish ? st->in2 : nullptr, st->col};
+    for (const Tensor* t : reads) {
+      if (!t || !t->bytes) continue;
+      if (t->bytes > arena_bytes_ || t->offset + t->bytes > arena_bytes_) return "tensor outside the arena at step " + st->name;
+      if (!ranges(t, is.i0, is.cn, [&](size_t b, size_t e, int image) { return owned(b, e, t->id, image); }))
+        return "step " + st->name + " (images from " + std::to_string(is.i0) + ") reads tensor " + std::to_string(t->id) + " after its storage was reused";
+    }
+    if (st->ws) write(st->ws->offset, st->ws->offset + st->ws->bytes, st->ws->id, -1);
+    const Tensor* o = st->out;
+    if (o && o->bytes) {
+      if (o->offset + o->bytes > arena_bytes_) return "tensor outside the arena at step " + st->name;
+      if (!ranges(o, is.i0, is.cn, [&](size_t b, size_t e, int image) { write(b, e, o->id, image); return true; }))
+        return "step " + st->name + " writes a sub-batch larger than its segment-local tensor";
+    }
+  }
+  return std::string();
 }
 
 bool FusedPlan::WeightsStale() const { return !weights_ || weights_->Stale(); }
@@ -712,16 +926,24 @@ void FusedPlan::Run() {
 
 void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stream) {
   Net<float>& net = *net_;
-  if (step_timing_ && events_.size() != steps_.size() + 1) {
+  if (step_timing_ && events_.size() != schedule_.size() + 1) {
     for (void* e : events_) dc_event_destroy(e);
-    events_.assign(steps_.size() + 1, nullptr);
+    events_.assign(schedule_.size() + 1, nullptr);
     for (void*& e : events_) DC_CHECK(dc_event_create(&e));
   }
-  size_t step_index = 0;
-  for (Step* st : steps_) {
-    if (step_timing_) DC_CHECK(dc_event_record(events_[step_index], stream));
-    const void* bp = blob_ptrs[step_index];
-    ++step_index;
+  // address of images [i0, ..) of a split tensor + the hi->lo plane distance a sub-batch launch must be told (0 = dense)
+  auto slice = [](const Tensor* t, int i0, int cn, long long* plane) -> void* {
+    *plane = 0;
+    if (cn == 0 || t->chunk_n > 0) return t->ptr;          // whole batch, or a segment-local tensor (holds this pass only)
+    *plane = static_cast<long long>(t->elems());
+    return static_cast<char*>(t->ptr) + static_cast<size_t>(i0) * (t->elems() / t->n) * 2;
+  };
+  size_t issue_index = 0;
+  for (const Issue& is : schedule_) {
+    Step* st = steps_[is.step];
+    if (step_timing_) DC_CHECK(dc_event_record(events_[issue_index], stream));
+    const void* bp = blob_ptrs[is.step];
+    ++issue_index;
     switch (st->type) {
       case Step::kConv1: {
         const float* x = static_cast<const float*>(bp);
@@ -736,15 +958,17 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
       case Step::kHeadGemm: {
         dc_conv_args a;
         memset(&a, 0, sizeof(a));
-        a.x = st->in->ptr; a.n = st->in->n; a.h = st->in->h; a.w = st->in->w; a.cin = st->in->c;
+        const bool conv = st->type == Step::kConvBN;
+        a.x = slice(st->in, is.i0, is.cn, &a.x_plane);
+        a.n = is.cn > 0 ? is.cn : st->in->n; a.h = st->in->h; a.w = st->in->w; a.cin = st->in->c;
         a.cout = st->cout; a.kh = st->kh; a.kw = st->kw; a.pad = st->pad; a.dilation = st->dil;
         a.w_packed = st->w_dev; a.scale = st->scale_dev; a.shift = st->shift_dev;
-        a.residual = st->in2 && st->type == Step::kConvBN ? st->in2->ptr : nullptr;
+        a.residual = st->in2 && conv ? slice(st->in2, is.i0, is.cn, &a.residual_plane) : nullptr;
         a.relu = st->relu;
-        a.out_f32_rows = st->type == Step::kHeadGemm ? 2 : 0;
+        a.out_f32_rows = conv ? 0 : 2;
         a.ldc = st->out->ld;
-        a.out = st->out->ptr;
-        a.stride = st->type == Step::kConvBN ? st->stride : 1;
+        a.out = conv ? slice(st->out, is.i0, is.cn, &a.out_plane) : st->out->ptr;
+        a.stride = conv ? st->stride : 1;
         a.splitk_workspace = splitk_ws_;
         a.splitk_workspace_bytes = splitk_ws_bytes_;
         DC_CHECK(dc_conv_forward(&a, stream));
@@ -768,23 +992,26 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
         break;
     }
   }
-  if (step_timing_) DC_CHECK(dc_event_record(events_[step_index], stream));
+  if (step_timing_) DC_CHECK(dc_event_record(events_[issue_index], stream));
 }
 
 std::vector<FusedPlan::StepInfo> FusedPlan::LastStepInfo() {
   static const char* kNames[] = {"Conv1", "ConvBN", "Subsample", "MaxPool", "HeadGemm", "HeadFinish", "ToBlob"};
   std::vector<StepInfo> out;
+  // a step of a chunked segment is issued once per pass: its time is the sum over its launches
+  std::vector<double> step_ms(steps_.size(), 0.0);
+  if (events_.size() == schedule_.size() + 1)
+    for (size_t k = 0; k < schedule_.size(); ++k) {
+      float ms = 0.f;
+      DC_CHECK(dc_event_elapsed_ms(events_[k], events_[k + 1], &ms));
+      step_ms[schedule_[k].step] += ms;
+    }
   for (size_t i = 0; i < steps_.size(); ++i) {
     const Step* st = steps_[i];
     StepInfo si;
     si.name = st->name;
     si.type = kNames[st->type];
-    si.ms = 0;
-    if (events_.size() == steps_.size() + 1) {
-      float ms = 0.f;
-      DC_CHECK(dc_event_elapsed_ms(events_[i], events_[i + 1], &ms));
-      si.ms = ms;
-    }
+    si.ms = step_ms[i];
     si.flops = 0;
     si.bytes = 0;
     auto tbytes = [](const Tensor* t) -> double {
@@ -827,11 +1054,21 @@ std::vector<FusedPlan::StepInfo> FusedPlan::LastStepInfo() {
 std::string FusedPlan::Describe() const {
   std::ostringstream s;
   static const char* kNames[] = {"Conv1", "ConvBN", "Subsample", "MaxPool", "HeadGemm", "HeadFinish", "ToBlob"};
-  s << steps_.size() << " steps, arena " << (arena_bytes_ >> 20) << " MiB, weights " << (weight_bytes() >> 20) << " MiB\n";
+  s << steps_.size() << " steps, " << schedule_.size() << " launch groups, arena " << (arena_bytes_ >> 20) << " MiB, weights " << (weight_bytes() >> 20) << " MiB\n";
+  for (const Segment& g : segments_)
+    s << "  segment " << steps_[g.first]->name << " .. " << steps_[g.last]->name << ": " << (g.bytes_per_image >> 10) << " KiB resident per image, "
+      << g.chunk << " of " << steps_[g.first]->in->n << " images per pass\n";
+  if (EnvOn("DC_DESCRIBE_SCHEDULE", false))      // one line per launch group, in launch order (profiling scripts map ncu rows to steps)
+    for (const Issue& is : schedule_)
+      s << "  issue " << kNames[steps_[is.step]->type] << " " << steps_[is.step]->name << " " << is.i0 << " " << is.cn << "\n";
+  int inplace = 0;
+  for (const Tensor* t : tensors_) inplace += t->gave_memory;
+  s << "  " << inplace << " block outputs written in place over their shortcut\n";
   for (const Step* st : steps_) {
     s << "  " << kNames[st->type] << " " << st->name;
     if (st->in) s << " in=" << st->in->n << "x" << st->in->c << "x" << st->in->h << "x" << st->in->w;
     if (st->type == Step::kConvBN) s << " k" << st->kh << " p" << st->pad << " d" << st->dil << " ->" << st->cout << (st->relu ? " relu" : "") << (st->in2 ? " +res" : "");
+    if (st->out && st->out->bytes) s << " out@" << st->out->offset << "+" << st->out->bytes << (st->out->chunk_n ? " (segment-local)" : "");
     s << "\n";
   }
   return s.str();

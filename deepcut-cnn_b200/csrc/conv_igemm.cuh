@@ -446,8 +446,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int dy = rr >> p.log2_tw, dx = rr & (p.TW - 1);
         if (yy0 + dy < p.Ho && xx0 + dx < p.Wo) {
           const __half* src = base + (pix0 + dy * p.Wo + dx) * p.Cout;
-          res_h[i] = __ldg(reinterpret_cast<const uint4*>(src));
-          res_l[i] = __ldg(reinterpret_cast<const uint4*>(src + p.res_plane));
+          // plain (coherent) loads: the output may alias the residual (in-place block output, dc_engine.cpp), which the
+          // read-only path must not see
+          res_h[i] = *reinterpret_cast<const uint4*>(src);
+          res_l[i] = *reinterpret_cast<const uint4*>(src + p.res_plane);
         }
       }
     };

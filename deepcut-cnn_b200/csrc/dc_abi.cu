@@ -116,10 +116,12 @@ void pack_row(int K, Get get, uint16_t* hi, uint16_t* lo, float* rowscale) {
 
 int tile_n_for(int cout) { return cout > 64 ? 128 : 64; }
 
-int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw, int th, int stride = 1) {
+// plane_elems: distance between the hi and lo planes in elements (0 = dense n*h*w*c; larger when the launch covers a
+// sub-batch of a bigger tensor)
+int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw, int th, int stride = 1, long long plane_elems = 0) {
   const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, 2};
   const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
-                                 (cuuint64_t)n * h * w * c * 2};
+                                 (cuuint64_t)(plane_elems > 0 ? plane_elems : (long long)n * h * w * c) * 2};
   // traversal stride s: the box spans tw*s x th*s input pixels of which every s-th is loaded (tw x th rows of smem)
   const cuuint32_t box[5] = {(cuuint32_t)dc::kBK, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), 1, 1};
   const cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
@@ -132,10 +134,10 @@ int encode_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c,
 }
 // Output (split NHWC) map for the epilogue's TMA stores: box = 32 channels x the 32-pixel sub-rectangle
 // one epilogue warp owns, SWIZZLE_64B to match the staging tile.
-int encode_out_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw) {
+int encode_out_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int tw, long long plane_elems = 0) {
   const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, 2};
   const cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
-                                 (cuuint64_t)n * h * w * c * 2};
+                                 (cuuint64_t)(plane_elems > 0 ? plane_elems : (long long)n * h * w * c) * 2};
   const int bw = tw < 32 ? tw : 32;
   const cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1, 1};
   const cuuint32_t es[5] = {1, 1, 1, 1, 1};
@@ -582,9 +584,13 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.scale = a->scale; p.shift = a->shift;
   p.res = static_cast<const __half*>(a->residual);
   const long long out_elems = static_cast<long long>(a->n) * ho * wo * a->cout;
-  p.res_plane = out_elems;
+  if ((a->x_plane && a->x_plane < static_cast<long long>(a->n) * a->h * a->w * a->cin) || (a->out_plane && a->out_plane < out_elems) ||
+      (a->residual_plane && a->residual_plane < out_elems))
+    return fail(DC_ERR_INVALID, "dc_conv_forward: a plane stride is smaller than the sub-batch it addresses");
+  if ((a->x_plane || a->out_plane) && a->out_f32_rows) return fail(DC_ERR_UNSUPPORTED, "dc_conv_forward: sub-batch plane strides apply to split output only");
+  p.res_plane = a->residual_plane > 0 ? a->residual_plane : out_elems;
   p.out = a->out;
-  p.out_plane = out_elems;
+  p.out_plane = a->out_plane > 0 ? a->out_plane : out_elems;
   p.ldc = a->ldc;
   p.relu = a->relu;
   p.out_mode = a->out_f32_rows == 2 ? dc::kOutF32RowsT : (a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC);
@@ -594,10 +600,10 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
-  if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH, stride)) return rc;
+  if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH, stride, a->x_plane)) return rc;
   if (!a->out_f32_rows) {
     // output geometry as the kernel indexes it (flattened for 1x1): [n][out_h][out_w][cout]
-    if (int rc = encode_out_map(&to, a->out, n, out_h, out_w, a->cout, p.TW)) return rc;
+    if (int rc = encode_out_map(&to, a->out, n, out_h, out_w, a->cout, p.TW, a->out_plane)) return rc;
   }
   // CTA pairs for the wide 1x1 convs (fewer operand bytes per SM, the lean epilogue); single CTAs with the fused
   // N = 2*BN MMA (conv_igemm.cuh) for the 3x3 convs and the 64-channel tiles, where they measure 3-15 % faster

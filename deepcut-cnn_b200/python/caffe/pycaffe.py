@@ -287,6 +287,13 @@ class Net(object):
     def weight_bytes(self):
         return lib.caffe_net_weight_bytes(self._h)
 
+    def describe_plan(self):
+        """The fused execution plan for the current input shapes (steps, L2-resident segments, launch groups, arena),
+        planned on the host: works without a GPU."""
+        buf = C.create_string_buffer(1 << 20)
+        check(lib.caffe_net_describe_plan(self._h, buf, len(buf)))
+        return buf.value.decode()
+
     def set_params(self, weights):
         """weights: {layer name: [arrays]} written through the param views (harness helper)."""
         params = self.params

@@ -73,6 +73,10 @@ int caffe_net_set_step_timing(void* net, int on);
 int caffe_net_num_steps(void* net);
 int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, double* flops, double* bytes, int max_steps);
 long long caffe_net_arena_bytes(void* net);
+/* Plans the fused execution for the net's CURRENT input shapes without touching a device (works in CPU mode): writes the plan's
+ * description (steps, L2-resident segments, launch groups, arena size) into out; returns 0, or 1 + caffe_last_error() when
+ * the topology does not fuse or the planner's own schedule check fails. */
+int caffe_net_describe_plan(void* net, char* out, int out_cap);
 long long caffe_net_weight_bytes(void* net);
 int caffe_insert_splits_text(const char* prototxt_text, char* out, int out_cap);   /* InsertSplits, insert_splits.cpp:12 */
 

@@ -122,6 +122,10 @@ typedef struct dc_conv_args {
                               * launches (see dc_set_split_k); without it such launches simply do not split.  No initialisation
                               * needed; must not be shared by launches that can run concurrently (one per stream). */
   size_t splitk_workspace_bytes;
+  /* Sub-batch launches (the L2-resident chunked schedule): x / out / residual may point at image i0 of a
+   * larger [2][N][..] tensor, n being the images this launch covers; the distance between the hi and the lo plane is then
+   * the FULL tensor's plane, given here in elements.  0 = dense (n*h*w*c of the tensor itself). */
+  long long x_plane, out_plane, residual_plane;
 } dc_conv_args;
 /* Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-24) =
  * im2col_gpu (util/im2col.cu:8-62) + cublasSgemm (util/math_functions.cu:13-27) per image, and the

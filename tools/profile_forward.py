@@ -17,6 +17,8 @@ ap.add_argument("--width", type=int, default=1280)
 ap.add_argument("--warm", type=int, default=2)
 ap.add_argument("--iters", type=int, default=1)
 ap.add_argument("--list-steps", action="store_true")
+ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the --iters forwards (ncu --profile-from-start off)")
+ap.add_argument("--schedule-out", default=None, help="write the plan description incl. the launch order (DC_DESCRIBE_SCHEDULE) here")
 args = ap.parse_args()
 
 import caffe  # noqa: E402
@@ -32,9 +34,20 @@ net = caffe.Net(path, caffe.TEST)
 net.set_params(synth.calibrated_weights(ptx.parse_file(path)))
 net.blobs["data"].reshape(args.batch, 3, args.height, args.width)
 net.blobs["data"].data[...] = synth.images(args.batch, args.height, args.width)
-for _ in range(args.warm + args.iters):
+for _ in range(args.warm):
     net.forward()
 caffe.sync()
+if args.schedule_out:
+    os.environ["DC_DESCRIBE_SCHEDULE"] = "1"
+    open(args.schedule_out, "w").write(net.describe_plan())
+if args.profiler_range:
+    import torch
+    torch.cuda.profiler.start()
+for _ in range(args.iters):
+    net.forward()
+caffe.sync()
+if args.profiler_range:
+    torch.cuda.profiler.stop()
 if args.list_steps:
     net.set_step_timing(True)
     net.forward()
