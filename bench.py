@@ -173,7 +173,15 @@ def time_cpu_reference(path, x1, warmup, steps, budget_s):
         # quarter-size image, rather than a handicap.
         blas = ctypes.CDLL(ref_caffe.LIB_PATH)
         try:
-            max_threads = int(blas.openblas_get_num_threads())
+            # the ceiling is the host's core count, NOT openblas_get_num_threads(): torch.distributed.run exports
+            # OMP_NUM_THREADS=1 to its workers, which OpenBLAS adopts at load time (round 1's N>1 reference lines ran on one
+            # thread); openblas_set_num_threads overrides it
+            try:
+                host_cores = len(os.sched_getaffinity(0))
+            except AttributeError:
+                host_cores = os.cpu_count() or 1
+            blas.openblas_set_num_threads(host_cores)
+            max_threads = max(1, min(host_cores, int(blas.openblas_get_num_threads())))
             hs, ws = max(64, H // 2), max(64, W // 2)
             small = synth.images(1, hs, ws)
             best = (None, max_threads)
@@ -187,8 +195,10 @@ def time_cpu_reference(path, x1, warmup, steps, budget_s):
                     best = (dt, t)
             cores = best[1]
             blas.openblas_set_num_threads(cores)
+            assert int(blas.openblas_get_num_threads()) == cores, "OpenBLAS did not take %d threads" % cores
+            assert cores > 1 or host_cores == 1, "the CPU reference would run single-threaded on a %d-core host" % host_cores
             est_image_s = best[0] * (H * W) / float(hs * ws)
-        except Exception:
+        except AttributeError:              # a BLAS without the openblas_* controls
             cores = os.cpu_count()
         kind, how = "reference", "reference CPU layers (oracle/_ref: im2col + OpenBLAS sgemm, %d BLAS threads = fastest of 8..all)" % cores
     else:
@@ -224,6 +234,8 @@ def run_reference(args, rank, world):
     one image of the workload (a bounded sample); rank 0 only, other ranks exit without work."""
     if rank != 0:
         return
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "GOTO_NUM_THREADS"):      # torchrun's per-worker thread cap is not the host's
+        os.environ.pop(v, None)
     synth = importlib.import_module("deepcut-cnn_b200.synth")
     path = build_net_files(args)
     x = synth.images(1, args.height, args.width)
@@ -475,7 +487,7 @@ def main():
     # ---- CPU baseline (oracle/_ref = the reference's CPU layers; numpy port if absent), rank 0 at N = 1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        dt, cpu_baseline, _, _ = time_cpu_reference(path, x[:1], 1, 2, budget_s=45.0)    # ~10-30 s of timed CPU work
+        dt, cpu_baseline, _, _ = time_cpu_reference(path, x[:1], 1, 3, budget_s=40.0)    # 1 warm-up + 3 timed, ~10-30 s of CPU work
         cpu_baseline["value"] = 1.0 / dt
 
     if rank == 0:

@@ -53,6 +53,9 @@ class FusedPlan {
   size_t weight_bytes() const { return weights_ ? weights_->bytes : 0; }
   int num_steps() const { return static_cast<int>(steps_.size()); }
   std::string Describe() const;
+  // per Net blob: 1 when Run() leaves the blob's current value in it (outputs; with materialisation the named intermediates
+  // that exist as tensors and the Split tops aliasing them)
+  std::vector<char> WrittenBlobs() const;
   // Per-step device timing: when enabled Run() brackets every step with CUDA events on the forward
   // stream (the reference's `caffe time` idiom, tools/caffe.cpp:302-388, per fused step instead of
   // per layer).  StepInfo gives the last run's duration and the step's algorithmic work.

@@ -81,6 +81,10 @@ class Net {
   void InvalidatePlan();
   void set_step_timing(bool on) { step_timing_ = on; }
   FusedPlan* plan() const { return plan_; }
+  // Does blob i hold the value of the LAST forward?  The fused plan writes only the net's outputs (and, on request, the
+  // named intermediates it can reconstruct); every other blob keeps whatever an earlier per-layer forward left there.  The
+  // reference fills every blob on every forward, so a caller reading a stale one must be told rather than handed old data.
+  bool blob_fresh(int i) const { return blob_fresh_.empty() || blob_fresh_[i] != 0; }
 
  protected:
   void AppendTop(const NetParameter& param, const int layer_id, const int top_id, set<string>* available_blobs, map<string, int>* blob_name_to_idx);
@@ -118,6 +122,7 @@ class Net {
   FusedPlan* plan_ = nullptr;
   shared_ptr<PlanWeightCache> plan_weights_;   // survives re-planning on reshape
   vector<vector<int> > plan_input_shapes_;
+  vector<char> blob_fresh_;          // empty = every blob is current (no fused forward has run yet)
 
   DISABLE_COPY_AND_ASSIGN(Net);
 };

@@ -38,6 +38,10 @@ class SyncedMemory {
   void to_cpu();
   void to_gpu();
   void alloc_cpu();
+  void mark_upload(void* stream);     // an async H2D from the pinned host buffer was queued on `stream`
+  void wait_upload();                 // ... and must have finished before the host may write that buffer again
+  void* upload_event_ = nullptr;
+  bool upload_pending_ = false;
   void* cpu_ptr_ = nullptr;
   void* gpu_ptr_ = nullptr;
   size_t size_ = 0;

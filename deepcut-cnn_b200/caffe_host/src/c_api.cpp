@@ -142,6 +142,7 @@ int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, doubl
 }
 long long caffe_net_arena_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->arena_bytes() : 0; }
 long long caffe_net_weight_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->weight_bytes() : 0; }
+int caffe_net_blob_fresh(void* net, int i) { return N(net)->blob_fresh(i) ? 1 : 0; }
 int caffe_net_describe_plan(void* net, char* out, int out_cap) {
   return Guard([&] {
     N(net)->Reshape();

@@ -159,7 +159,15 @@ struct Matcher {
     int bn = InPlaceNext(t, "BatchNorm");
     if (bn >= 0) t = top_t[bn][0];
     int sc = InPlaceNext(t, "Scale");
-    if (sc >= 0) t = top_t[sc][0];
+    if (sc >= 0) {
+      // only the per-channel form folds into the epilogue: gamma (and beta) of shape {Cout} applied along axis 1
+      Layer<float>* sl = net.layers()[sc].get();
+      const ScaleParameter& sp = sl->layer_param().scale_param();
+      const bool per_channel = sl->blobs().size() >= 1 && sl->blobs()[0]->count() == conv->num_output() && sl->blobs()[0]->num_axes() == 1 &&
+                               sp.axis() == 1 && (sl->blobs().size() < 2 || sl->blobs()[1]->count() == conv->num_output());
+      if (per_channel) t = top_t[sc][0];
+      else sc = -1;
+    }
     int rl = InPlaceNext(t, "ReLU");
     if (rl >= 0) {
       if (net.layers()[rl]->layer_param().relu_param().negative_slope() != 0.f) rl = -1;   // leaky: leave to the per-layer path
@@ -325,6 +333,15 @@ struct Matcher {
     if (heads.empty()) return Fail("no head matched");
     int ctot = 0;
     for (const Head& h : heads) ctot += As<ConvBase>(net.layers()[h.deconv].get())->num_output();
+    // what the merged channel-major GEMMs (dc_conv_forward, out_f32_rows = 2) need: 128-row weight tiles, i.e. more than 64
+    // merged outputs, and inputs in whole 64-channel K chunks.  A net trimmed to e.g. the part + locref heads (14 + 28 rows)
+    // runs layer by layer instead of failing inside the plan.
+    // The merged channel-major GEMMs (dc_conv_forward, out_f32_rows = 2) run 128-row weight tiles: a net trimmed to e.g. the
+    // part + locref heads (14 + 28 outputs; callers that never read next_pred, estimate_pose.py:231) gets its skip matrix
+    // zero-padded to a full tile instead of being refused.
+    const int skip_rows = std::max(ctot, 65);
+    if (x5->kind != FusedPlan::Tensor::kSplit || x5->c % 64 != 0 || x3->c % 64 != 0)
+      return Fail("head inputs must be split activations with a multiple of 64 channels");
     const int h5 = x5->h, w5 = x5->w, h3 = x3->h, w3 = x3->w;
     if (!(2 * h5 + 1 > h3 && 2 * w5 + 1 > w3 && h3 <= 2 * h5 + 1)) return Fail("head geometry: crop larger than the deconvolution output");
     // merged deconv GEMM -> col rows, merged 1x1 GEMM -> skip rows
@@ -334,10 +351,10 @@ struct Matcher {
     col->ld = round32(static_cast<long long>(x5->n) * h5 * w5);
     FusedPlan::Step* g1 = AddStep(FusedPlan::Step::kHeadGemm, "heads/deconv_gemm");
     g1->in = x5; g1->out = col; g1->deconv_rows = true; g1->cout = ctot * 9;
-    FusedPlan::Tensor* srows = NewInternal(FusedPlan::Tensor::kF32Rows, 1, 1, dc_packed_rows(ctot), 1);
+    FusedPlan::Tensor* srows = NewInternal(FusedPlan::Tensor::kF32Rows, 1, 1, dc_packed_rows(skip_rows), 1);
     srows->ld = round32(static_cast<long long>(x3->n) * h3 * w3);
     FusedPlan::Step* g2 = AddStep(FusedPlan::Step::kHeadGemm, "heads/skip_gemm");
-    g2->in = x3; g2->out = srows; g2->deconv_rows = false; g2->cout = ctot;
+    g2->in = x3; g2->out = srows; g2->deconv_rows = false; g2->cout = skip_rows;
     int off = 0;
     for (const Head& h : heads) {
       g1->merged_layers.push_back(h.deconv);
@@ -499,7 +516,10 @@ void FusedPlan::PlanSchedule() {
   }
   for (Tensor* t : tensors_) { t->alloc_step = t->def_step; t->free_step = t->last_step; }
 
-  const size_t budget = EnvMiB("DC_L2_CHUNK_MB", 80u << 20);
+  // Off by default: measured on B200 (profiles/r2_chunk_sweep.md) the chunked schedule cuts a forward's DRAM traffic from 74.6 GB
+  // to 32.8 GB, yet the step gets SLOWER -- these convs are bound by per-SM operand latency and wave quantisation, not by HBM,
+  // and a sub-batch launch has 3-16x fewer tiles to hide either.
+  const size_t budget = EnvMiB("DC_L2_CHUNK_MB", 0);
   std::vector<int> forced;
   if (const char* e = getenv("DC_CHUNK_PLAN")) {
     std::stringstream ss(e);
@@ -842,7 +862,9 @@ void FusedPlan::UploadWeights(Net<float>& net) {
       int ctot = 0;
       for (int l : st->merged_layers) ctot += As<ConvBase>(net.layers()[l].get())->num_output();
       const int taps = st->deconv_rows ? 9 : 1;
-      std::vector<float> wcat(static_cast<size_t>(cin) * ctot * taps);
+      const int real = ctot;
+      if (!st->deconv_rows) ctot = std::max(ctot, st->cout);        // skip matrix zero-padded to a 128-row tile (MatchHeads)
+      std::vector<float> wcat(static_cast<size_t>(cin) * ctot * taps, 0.f);
       std::vector<float> bias(ctot, 0.f);
       int off = 0;
       for (int l : st->merged_layers) {
@@ -869,7 +891,7 @@ void FusedPlan::UploadWeights(Net<float>& net) {
       if (!st->deconv_rows) {
         // both biases of a head land on the same output element: fold the deconvolution's into the
         // skip GEMM's shift (the deconv GEMM step precedes this one and recorded its biases there)
-        for (int c = 0; c < ctot; ++c) shift[c] = bias[c];
+        for (int c = 0; c < real; ++c) shift[c] = bias[c];
         for (Step* other : steps_)
           if (other->type == Step::kHeadGemm && other->deconv_rows) {
             int o2 = 0;
@@ -907,7 +929,16 @@ void FusedPlan::Run() {
     if (graph_ != nullptr && ptrs != graph_ptrs_) { dc_graph_destroy(graph_); graph_ = nullptr; }
     if (graph_ == nullptr) {
       if (dc_graph_begin(stream) == 0) {
-        IssueSteps(ptrs, stream);
+        try {
+          IssueSteps(ptrs, stream);
+        } catch (...) {
+          // a launch was refused mid-capture (FatalError under the Python binding): leave capture mode before the error
+          // travels on, or every later call on this stream would fail with "operation not permitted when stream is capturing"
+          void* dead = nullptr;
+          if (dc_graph_end(stream, &dead) == 0 && dead) dc_graph_destroy(dead);
+          graph_failed_ = true;
+          throw;
+        }
         if (dc_graph_end(stream, &graph_) != 0) { graph_ = nullptr; graph_failed_ = true; LOG(WARNING) << "CUDA graph capture failed (" << DcLastError() << "); launching step by step"; }
         else graph_ptrs_ = ptrs;
       } else {
@@ -1049,6 +1080,16 @@ std::vector<FusedPlan::StepInfo> FusedPlan::LastStepInfo() {
     out.push_back(si);
   }
   return out;
+}
+
+std::vector<char> FusedPlan::WrittenBlobs() const {
+  std::vector<char> w(net_->blobs().size(), 0);
+  for (const Step* st : steps_)
+    if (st->out_blob >= 0) w[st->out_blob] = 1;
+  for (int l : split_layers_)             // Split tops alias their bottom (zero-copy), in layer order
+    if (w[net_->bottom_ids(l)[0]])
+      for (int t : net_->top_ids(l)) w[t] = 1;
+  return w;
 }
 
 std::string FusedPlan::Describe() const {

@@ -181,6 +181,13 @@ Dtype Net<Dtype>::ForwardFromTo(int start, int end) {
   CHECK_LT(end, (int)layers_.size());
   Dtype loss = 0;
   for (int i = start; i <= end; ++i) {
+    // a per-layer (partial) forward after a fused one: its bottoms must be values the last forward really left in the blobs
+    if (!blob_fresh_.empty()) {
+      for (int b : bottom_id_vecs_[i])
+        CHECK(blob_fresh_[b]) << "layer " << layer_names_[i] << " reads blob " << blob_names_[b] << ", which the last (fused) forward did not "
+                              << "materialise: call materialize_intermediates(true) or set_fusion(false) before forwarding from the middle of the net";
+      for (int t : top_id_vecs_[i]) blob_fresh_[t] = 1;
+    }
     loss += layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
     if (debug_info_) ForwardDebugInfo(i);
   }
@@ -207,6 +214,8 @@ const vector<Blob<Dtype>*>& Net<Dtype>::ForwardPrefilled(Dtype* loss) {
       plan_->set_step_timing(step_timing_);
       plan_->Run();
       fused_last_forward_ = true;
+      blob_fresh_ = plan_->WrittenBlobs();
+      for (int b : net_input_blob_indices_) blob_fresh_[b] = 1;
       last_launches_ = dc_launch_count() - launches_before;
       return net_output_blobs_;
     }

@@ -7,7 +7,25 @@
 
 namespace caffe {
 
+// An upload from pinned memory is asynchronous (the reference's is a synchronous cudaMemcpy, syncedmem.cpp:61-69): until it has
+// finished the host buffer still belongs to the DMA engine.  Every path that lets the host WRITE the buffer again (or frees
+// it) first waits for the event recorded behind the copy -- `blob.data[...] = a; net.forward(); blob.data[...] = b` must not
+// change what the first forward reads.
+void SyncedMemory::mark_upload(void* stream) {
+  if (!cpu_malloc_use_cuda_) return;         // pageable source: the caller synchronises the stream
+  if (upload_event_ == nullptr) DC_CHECK(dc_event_create(&upload_event_));
+  DC_CHECK(dc_event_record(upload_event_, stream));
+  upload_pending_ = true;
+}
+void SyncedMemory::wait_upload() {
+  if (!upload_pending_) return;
+  DC_CHECK(dc_event_sync(upload_event_));
+  upload_pending_ = false;
+}
+
 SyncedMemory::~SyncedMemory() {
+  if (upload_pending_) dc_event_sync(upload_event_);
+  if (upload_event_) dc_event_destroy(upload_event_);
   if (cpu_ptr_ && own_cpu_data_) {
     if (cpu_malloc_use_cuda_) dc_free_host(cpu_ptr_);
     else free(cpu_ptr_);
@@ -64,6 +82,7 @@ inline void SyncedMemory::to_gpu() {
       }
       DC_CHECK(dc_memcpy_async(gpu_ptr_, cpu_ptr_, size_, DC_H2D, Caffe::stream()));
       if (!cpu_malloc_use_cuda_) DC_CHECK(dc_stream_sync(Caffe::stream()));   // pageable source
+      else mark_upload(Caffe::stream());
       head_ = SYNCED;
       break;
     case HEAD_AT_GPU:
@@ -76,6 +95,7 @@ const void* SyncedMemory::cpu_data() { to_cpu(); return cpu_ptr_; }
 
 void SyncedMemory::set_cpu_data(void* data) {
   CHECK(data);
+  wait_upload();
   if (own_cpu_data_ && cpu_ptr_) { if (cpu_malloc_use_cuda_) dc_free_host(cpu_ptr_); else free(cpu_ptr_); }
   cpu_ptr_ = data;
   ++host_epoch_;
@@ -94,7 +114,7 @@ void SyncedMemory::set_gpu_data(void* data) {
   own_gpu_data_ = false;
 }
 
-void* SyncedMemory::mutable_cpu_data() { to_cpu(); head_ = HEAD_AT_CPU; ++host_epoch_; return cpu_ptr_; }
+void* SyncedMemory::mutable_cpu_data() { to_cpu(); wait_upload(); head_ = HEAD_AT_CPU; ++host_epoch_; return cpu_ptr_; }
 void* SyncedMemory::mutable_gpu_data() { to_gpu(); head_ = HEAD_AT_GPU; return gpu_ptr_; }
 
 void* SyncedMemory::overwrite_gpu_data() {
@@ -111,9 +131,12 @@ void SyncedMemory::async_gpu_push(void* stream) {
   CHECK(head_ == HEAD_AT_CPU);
   if (gpu_ptr_ == nullptr) {
     DC_CHECK(dc_malloc(&gpu_ptr_, size_ ? size_ : 1));
+    gpu_device_ = Caffe::device();
     own_gpu_data_ = true;
   }
   DC_CHECK(dc_memcpy_async(gpu_ptr_, cpu_ptr_, size_, DC_H2D, stream));
+  if (!cpu_malloc_use_cuda_) DC_CHECK(dc_stream_sync(stream));
+  else mark_upload(stream);
   head_ = SYNCED;
 }
 

@@ -371,6 +371,10 @@ int dc_event_record(void* event, void* stream) {
   DC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
   return DC_OK;
 }
+int dc_event_sync(void* event) {
+  DC_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+  return DC_OK;
+}
 int dc_event_elapsed_ms(void* start, void* stop, float* ms) {
   DC_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
   DC_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));

@@ -49,7 +49,7 @@ def _load():
         "caffe_net_step_info": (ci, [vp, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), ci]),
         "caffe_net_arena_bytes": (C.c_longlong, [vp]), "caffe_net_weight_bytes": (C.c_longlong, [vp]),
-        "caffe_net_describe_plan": (ci, [vp, C.c_char_p, ci]),
+        "caffe_net_describe_plan": (ci, [vp, C.c_char_p, ci]), "caffe_net_blob_fresh": (ci, [vp, ci]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -2,18 +2,20 @@
 _caffe.cpp:225-276): OrderedDict views `blobs` and `params`, `inputs`/`outputs`, `forward(**kwargs)`,
 `Blob.data` as a zero-copy NumPy view of mutable_cpu_data() that keeps the blob alive."""
 import ctypes as C
+import weakref
 from collections import OrderedDict
 
 import numpy as np
 
 from . import _caffe
-from ._caffe import lib, check, check_ptr
+from ._caffe import lib, check, check_ptr, CaffeError
 
 
 class Blob(object):
-    def __init__(self, handle, owner=None):
+    def __init__(self, handle, net=None, index=-1):
         self._h = handle
-        self._owner = owner        # keeps the Net python object alive for name tables only
+        self._net = weakref.ref(net) if net is not None else None      # activation blobs know their Net (weakly: the blob
+        self._index = index                                           # memory may outlive it, test_net.py:48-60)
 
     def __del__(self):
         try:
@@ -56,8 +58,16 @@ class Blob(object):
         # the array holds a reference to this Blob object, which holds the shared_ptr handle
         return _BlobArray(a, self)
 
+    def _check_fresh(self):
+        net = self._net() if self._net is not None else None
+        if net is not None and not lib.caffe_net_blob_fresh(net._h, self._index):
+            raise CaffeError("blob '%s' was not written by the last forward: the fused B200 plan materialises only the net's outputs. "
+                             "Ask for it -- net.forward(blobs=['%s']) -- or call net.materialize_intermediates(True) / "
+                             "net.set_fusion(False) first." % (net._blob_names[self._index], net._blob_names[self._index]))
+
     @property
     def data(self):
+        self._check_fresh()
         return self._view(lib.caffe_blob_mutable_cpu_data(self._h))
 
     @property
@@ -82,7 +92,7 @@ class Blob(object):
         """SyncedMemory::head() of the data (include/caffe/syncedmem.hpp:65-66) as its enumerator's name."""
         h = lib.caffe_blob_data_head(self._h)
         if h < 0:
-            raise RuntimeError(last_error())
+            raise CaffeError(lib.caffe_last_error().decode(errors="replace"))
         return self.HEADS[h]
 
 
@@ -164,7 +174,7 @@ class Net(object):
         h = self._h
         self._blob_names = [lib.caffe_net_blob_name(h, i).decode() for i in range(lib.caffe_net_num_blobs(h))]
         self._layer_names = [lib.caffe_net_layer_name(h, i).decode() for i in range(lib.caffe_net_num_layers(h))]
-        self._blobs = [Blob(check_ptr(lib.caffe_net_blob(h, i))) for i in range(len(self._blob_names))]
+        self._blobs = [Blob(check_ptr(lib.caffe_net_blob(h, i)), self, i) for i in range(len(self._blob_names))]
         self.layers = [Layer(self, i) for i in range(len(self._layer_names))]
         self._inputs = [lib.caffe_net_input_index(h, i) for i in range(lib.caffe_net_num_inputs(h))]
         self._outputs = [lib.caffe_net_output_index(h, i) for i in range(lib.caffe_net_num_outputs(h))]
@@ -222,7 +232,12 @@ class Net(object):
                     raise Exception("Input is not batch sized")
                 self.blobs[in_].data[...] = blob
         if start is None and end is None:
-            check(lib.caffe_net_forward(self._h))
+            if set(blobs) - set(self.outputs) - set(self.inputs):
+                # the caller wants intermediates (pycaffe.py:62-108 returns any named blob): the reference fills every blob on
+                # every forward, the fused plan only the outputs -- run this call layer by layer, which materialises everything
+                self._forward(0, len(self.layers) - 1)
+            else:
+                check(lib.caffe_net_forward(self._h))
             outputs = set(self.outputs + blobs)
         else:
             start_ind = 0 if start is None else self._layer_names.index(start)

@@ -73,6 +73,9 @@ int caffe_net_set_step_timing(void* net, int on);
 int caffe_net_num_steps(void* net);
 int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, double* flops, double* bytes, int max_steps);
 long long caffe_net_arena_bytes(void* net);
+/* 1 when blob i holds the value of the last forward; 0 for an intermediate the fused plan did not write (the reference fills
+ * every blob each forward, net.cpp:565-581 -- the shim raises instead of returning stale data). */
+int caffe_net_blob_fresh(void* net, int i);
 /* Plans the fused execution for the net's CURRENT input shapes without touching a device (works in CPU mode): writes the plan's
  * description (steps, L2-resident segments, launch groups, arena size) into out; returns 0, or 1 + caffe_last_error() when
  * the topology does not fuse or the planner's own schedule check fails. */

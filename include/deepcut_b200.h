@@ -65,6 +65,7 @@ int dc_event_create(void** event);
 int dc_event_destroy(void* event);
 int dc_event_record(void* event, void* stream);
 int dc_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
+int dc_event_sync(void* event);                                /* host waits until the work recorded before `event` is done */
 
 /* CUDA-graph capture of a launch sequence issued through this ABI on `stream` (per input shape: the fused
  * plan replays ~164 launches, incl. their cluster / programmatic-dependent-launch attributes, from one

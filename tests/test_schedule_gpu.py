@@ -38,11 +38,11 @@ def test_sub_batch_launch_equals_full_launch(case):
     wt = (rng.standard_normal((co, ci, k, k)) * (2.0 / (ci * k * k)) ** 0.5).astype(np.float32)
     a = rng.uniform(0.5, 1.5, co).astype(np.float32)
     b = rng.normal(0, 0.1, co).astype(np.float32)
-    full = dcutil.np_split(gpuharness.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True, split_k_workspace=False))
+    full = gpuharness.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True, split_k_workspace=False)       # fp32 NCHW = hi + lo
     part = gpuharness.conv_bn_subbatch(x, wt, a, b, i0, cn, pad=pad, dil=dil, relu=True)
     sel = np.zeros(n, bool)
     sel[i0:i0 + cn] = True
-    assert np.array_equal(part[:, sel].view(np.uint16), full[:, sel].view(np.uint16))
+    assert np.array_equal(dcutil.np_join(part[:, sel]), full[sel])
     assert np.isnan(part[:, ~sel].astype(np.float32)).all(), "the launch wrote outside its sub-batch"
 
 
@@ -57,10 +57,10 @@ def test_block_output_in_place_over_the_shortcut(co, k, h, w):
     wt = (rng.standard_normal((co, ci, k, k)) * (2.0 / (ci * k * k)) ** 0.5).astype(np.float32)
     a = rng.uniform(0.5, 1.5, co).astype(np.float32)
     b = rng.normal(0, 0.1, co).astype(np.float32)
-    want = dcutil.np_split(gpuharness.conv_bn(x, wt, a, b, pad=k // 2, relu=True, residual_nchw=r, split_k_workspace=False))
+    want = gpuharness.conv_bn(x, wt, a, b, pad=k // 2, relu=True, residual_nchw=r, split_k_workspace=False)
     got = gpuharness.conv_bn_subbatch(x, wt, a, b, 1, 2, pad=k // 2, relu=True, residual_nchw=r, inplace=True)
     rs = dcutil.np_split(r)
-    assert np.array_equal(got[:, 1:3].view(np.uint16), want[:, 1:3].view(np.uint16))
+    assert np.array_equal(dcutil.np_join(got[:, 1:3]), want[1:3])
     for i in (0, 3):      # images outside the sub-batch still hold the shortcut
         assert np.array_equal(got[:, i].view(np.uint16), rs[:, i].view(np.uint16))
 
