@@ -55,8 +55,10 @@ def parse_args():
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--model", default="152", choices=["152", "101"])
-    ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3"],
-                    help="BASELINE.json configs: cfg1 = batch 1 3x512x512, cfg2 = batch 16 3x720x1280 (default), cfg3 = batch 16/GPU 3x512x512")
+    ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3", "batch128_512"],
+                    help="BASELINE.json configs[i]: cfg1 = batch 1 3x512x512, cfg2 = batch 16 3x720x1280 (default), cfg3 = batch128_512 = "
+                         "batch 16/GPU 3x512x512 (128 images on 8 GPUs, sharded per image; with --gpus N > 1 the line carries the NCCL "
+                         "scatter/gather `exchange` record).  configs[4] (the scale pyramid) is tools/pyramid_bench.py")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency-config", action="store_true",
                     help="skip the extra single-image measurement (BASELINE configs[1]: batch 1, 3x512x512) the default workload reports")
@@ -257,7 +259,7 @@ def main():
     args = parse_args()
     if args.workload == "cfg1":
         args.batch, args.height, args.width = 1, 512, 512
-    elif args.workload == "cfg3":
+    elif args.workload in ("cfg3", "batch128_512"):
         args.batch, args.height, args.width = 16, 512, 512
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -342,27 +344,17 @@ def main():
     h2d = B * 3 * H * W * 4
     d2h = (prob.count + loc.count) * 4
     exchange = dist is not None and args.e2e_mode == "exchange"
-    if not exchange:
-        # every rank serves its own requests from its own pinned host buffers (one PCIe link per GPU): the data-parallel
-        # deployment of this path.  h2d / d2h below are whole-job bytes per step.
-        h2d, d2h = h2d * world, d2h * world
+    # every rank serves its own requests from its own pinned host buffers (one PCIe link per GPU): the data-parallel
+    # deployment of this path.  h2d / d2h below are whole-job bytes per step.
+    h2d, d2h = h2d * world, d2h * world
 
-        def e2e_step():
-            net.blobs["data"].data          # host write access: the pinned host copy is authoritative again -> H2D next forward
-            net.forward()
-            prob.data                       # D2H + sync (what estimate_pose.py reads)
-            loc.data
-    else:
-        dmod = importlib.import_module("deepcut-cnn_b200.dist")
-        ex = dmod.BatchExchange(dist, rank, world, (B, 3, H, W), {"prob": prob.shape, "loc_pred": loc.shape}, x if rank == 0 else None)
-        h2d, d2h = ex.h2d_bytes, ex.d2h_bytes
-
-        def e2e_step():
-            ex.scatter_into(net.blobs["data"], L, stream)
-            net.forward()
-            ex.gather_from({"prob": prob, "loc_pred": loc}, L, stream)
-    e2e_mode = "rank 0 owns the global batch: NCCL scatter / gather over NVLink around each forward" if exchange else "serial"
-    if not exchange and args.e2e_inflight > 1:
+    def e2e_step():
+        net.blobs["data"].data          # host write access: the pinned host copy is authoritative again -> H2D next forward
+        net.forward()
+        prob.data                       # D2H + sync (what estimate_pose.py reads)
+        loc.data
+    e2e_mode = "serial"
+    if args.e2e_inflight > 1:
         # Double-buffered serving through the same public API: a second Net (own host thread, own stream, own arena;
         # weights packed from the same blobs) keeps the GPU busy while the first one's H2D / D2H copies are in flight.
         import threading
@@ -425,6 +417,31 @@ def main():
             e2e_step()
         _, e2e_wall_ms = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (e2e_wall_ms / 1e3)     # host wall clock: includes every copy and sync
+
+    # ---- N > 1: the batch exchange the north_star names -- rank 0 owns the WHOLE host batch (uint8 images), NCCL scatter over
+    # NVLink into every rank's `data` blob, forward, NCCL gather of prob + loc_pred back to rank 0's pinned host memory;
+    # step k+1's upload + scatter and step k's gather overlap the forwards (deepcut-cnn_b200/dist.py PipelinedExchange)
+    exchange_rec = None
+    if dist is not None:
+        dmod = importlib.import_module("deepcut-cnn_b200.dist")
+        host_u8 = synth.images_u8(world * B, H, W, seed=20160505) if rank == 0 else None
+        ex = dmod.PipelinedExchange(dist, rank, world, net, libdc, B, H, W, ["prob", "loc_pred"], host_u8=host_u8)
+        ex.run(3)
+        barrier()
+        t0 = time.time()
+        ex.run(args.steps)
+        ex_wall_ms = (time.time() - t0) * 1e3
+        tmax = torch.tensor([ex_wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ex_wall_ms = float(tmax[0])
+        exchange_rec = {"value": world * B * args.steps / (ex_wall_ms / 1e3), "unit": "images/s", "ms_per_step": ex_wall_ms / args.steps,
+                        "h2d_bytes_per_step": int(ex.h2d_bytes), "d2h_bytes_per_step": int(ex.d2h_bytes),
+                        "nvlink_bytes_per_step": int(ex.nvlink_bytes), "steps": args.steps,
+                        "mode": "rank 0 owns the global host batch (uint8 HWC): H2D on rank 0, NCCL scatter, on-device u8->float, "
+                                "forward, NCCL gather of prob+loc_pred to rank 0, D2H; scatter k+1 / gather k overlap forward k"}
+        if exchange:
+            e2e_value, e2e_wall_ms, h2d, d2h, e2e_mode = exchange_rec["value"], ex_wall_ms, ex.h2d_bytes, ex.d2h_bytes, exchange_rec["mode"]
+        del ex
     # ---- per-step roofline pass (separate from the timed region: events around every step)
     roofline = None
     report = None
@@ -499,7 +516,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred", "mode": e2e_mode},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency,
+                "exchange": exchange_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency,
                 "wall_ms_per_step": wall_ms / args.steps, "arena_mib": net.arena_bytes >> 20, "weights_mib": net.weight_bytes >> 20}
         emit(line)
     if dist is not None:

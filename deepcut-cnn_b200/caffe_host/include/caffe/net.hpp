@@ -62,6 +62,10 @@ class Net {
   bool has_layer(const string& layer_name) const;
   const shared_ptr<Layer<Dtype> > layer_by_name(const string& layer_name) const;
   void set_debug_info(const bool value) { debug_info_ = value; }
+  // What the last debug_info forward printed (net.cpp:648-735 of the reference logs "[Forward] Layer L, top blob B data: mean|x|"
+  // per top): kept so callers and tests can compare the probes blob by blob instead of parsing the log.
+  struct DebugRecord { string layer, blob; double mean_abs; };
+  const vector<DebugRecord>& debug_log() const { return debug_log_; }
 
   static void FilterNet(const NetParameter& param, NetParameter* param_filtered);
   static bool StateMeetsRule(const NetState& state, const NetStateRule& rule, const string& layer_name);
@@ -111,6 +115,7 @@ class Net {
   vector<shared_ptr<Blob<Dtype> > > params_;
   vector<Blob<Dtype>*> learnable_params_;
   bool debug_info_ = false;
+  vector<DebugRecord> debug_log_;
   NetParameter filtered_param_;     // post FilterNet + InsertSplits
 
   bool fusion_ = true;

@@ -142,6 +142,23 @@ int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, doubl
 }
 long long caffe_net_arena_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->arena_bytes() : 0; }
 long long caffe_net_weight_bytes(void* net) { return N(net)->plan() ? (long long)N(net)->plan()->weight_bytes() : 0; }
+int caffe_net_set_debug_info(void* net, int on) { return Guard([&] { N(net)->set_debug_info(on != 0); }); }
+int caffe_net_debug_info(void* net, char* names, int names_cap, double* mean_abs, int max_records) {
+  int n = -1;
+  Guard([&] {
+    const auto& log = N(net)->debug_log();
+    CHECK_LE((int)log.size(), max_records);
+    std::string all;
+    for (size_t i = 0; i < log.size(); ++i) {
+      all += log[i].layer + " " + log[i].blob + "\n";
+      mean_abs[i] = log[i].mean_abs;
+    }
+    CHECK_LT((int)all.size(), names_cap);
+    memcpy(names, all.c_str(), all.size() + 1);
+    n = static_cast<int>(log.size());
+  });
+  return n;
+}
 int caffe_net_blob_fresh(void* net, int i) { return N(net)->blob_fresh(i) ? 1 : 0; }
 int caffe_net_describe_plan(void* net, char* out, int out_cap) {
   return Guard([&] {

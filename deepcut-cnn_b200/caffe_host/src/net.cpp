@@ -180,6 +180,7 @@ Dtype Net<Dtype>::ForwardFromTo(int start, int end) {
   CHECK_GE(start, 0);
   CHECK_LT(end, (int)layers_.size());
   Dtype loss = 0;
+  if (debug_info_) debug_log_.clear();
   for (int i = start; i <= end; ++i) {
     // a per-layer (partial) forward after a fused one: its bottoms must be values the last forward really left in the blobs
     if (!blob_fresh_.empty()) {
@@ -237,7 +238,9 @@ void Net<Dtype>::ForwardDebugInfo(const int layer_id) {
   for (size_t top_id = 0; top_id < top_vecs_[layer_id].size(); ++top_id) {
     const Blob<Dtype>& blob = *top_vecs_[layer_id][top_id];
     const Dtype mean_abs = blob.count() ? blob.asum_data() / blob.count() : 0;
-    LOG(WARNING) << "    [Forward] Layer " << layer_names_[layer_id] << ", top blob " << blob_names_[top_id_vecs_[layer_id][top_id]] << " data: " << mean_abs;
+    LOG(INFO) << "    [Forward] Layer " << layer_names_[layer_id] << ", top blob " << blob_names_[top_id_vecs_[layer_id][top_id]] << " data: " << mean_abs;
+    DebugRecord r = {layer_names_[layer_id], blob_names_[top_id_vecs_[layer_id][top_id]], static_cast<double>(mean_abs)};
+    debug_log_.push_back(r);
   }
 }
 

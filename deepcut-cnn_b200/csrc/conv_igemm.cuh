@@ -81,14 +81,9 @@ struct ConvCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static_assert(BN == 64 || BN == 128, "4 accumulators of BN columns must fit 512 TMEM columns");
   static_assert(EW == 8 || (EW == 16 && BN == 128), "the 16-warp epilogue owns one 32-channel chunk per warp: BN = 128");
-  // EW = 16 (epilogue-bound layers, K <= 512): two operand stages are enough to keep a K loop of 4-8 steps fed, and the
-  // shared memory they free double-buffers the epilogue's staging tiles (below)
-  static constexpr int kStages = EW == 16 ? 2 : (CG == 2 ? 4 : (BN >= 128 ? 3 : 4));
+  static constexpr int kStages = (CG == 2 ? 4 : (BN >= 128 ? 3 : 4)) - (EW == 16 ? 1 : 0);
   static constexpr int kTmemCols = 4 * BN;                         // 2 x (main, cross)
-  // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo} = 4 KB; the lean epilogue has TWO such tiles per warp so that the
-  // residual of tile i+1 streams in (cp.async) while tile i is converted in place and its TMA stores drain
-  static constexpr int kStagingPerWarp = EW == 16 ? 8192 : 4096;
-  static constexpr int kStagingBytes = EW * kStagingPerWarp;
+  static constexpr int kStagingBytes = EW * 4096;        // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo}
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -286,51 +281,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (EW == 16) {
     // ------------------------------------------------------------ lean epilogue (warps 2..17), split-NHWC only
-    // One 32-pixel x 32-channel chunk per warp per tile, accumulators read 16 columns at a time.  Each warp owns TWO 4 KB
-    // staging tiles and alternates between them: at the top of tile i it starts the cp.async copy of tile i+1's residual
-    // chunk into the other tile (free: tile i-1's TMA stores have been read out of it), then adds tile i's residual -- in
-    // shared memory since one tile period -- converts in place and hands the tile to two TMA stores it does not wait for.
-    // With a single staging tile (round 1) the residual fetch could only start after the stores had drained, so its full
-    // L2/HBM latency sat on every tile's critical path: 4.6 us per tile against 2 us of MMAs (profiles/r2_ncu_summary.md).
+    // (Round 2 tried two staging tiles per warp -- the residual of tile i+1 streaming in while tile i is converted -- paid for
+    // with one operand stage (227 KB of shared memory hold 3 x 48 KB stages + 64 KB of staging, or 2 + 128): 112.7 -> 132.6 us
+    // on res4's 2c.  The sampled stalls moved from the epilogue to the MMA issuer waiting on `full` barriers: these K <= 512
+    // layers are bound by operand bytes in flight per SM, not by the epilogue chain; profiles/r2_ncu_summary.md.)
+    // One 32-pixel x 32-channel chunk per warp per tile.  The residual chunk is copied global -> staging by
+    // cp.async as soon as the previous tile's TMA stores have drained the staging tile, i.e. while the
+    // next accumulator is still being computed; accumulators are read 16 columns at a time.
     const int q = warp & 3;
     const int c0 = ((warp - 2) >> 2) * 32;
-    uint8_t* stg_pair = staging_all + (warp - 2) * Cfg::kStagingPerWarp;
+    uint8_t* stg = staging_all + (warp - 2) * 4096;
     const int piece = lane & 3;
     const int own_sw = (lane >> 1) & 3;
     const bool has_res = p.res != nullptr;
-    // always commits one cp.async group (possibly empty), so "all but the newest group" is exactly "this tile's residual"
-    auto issue_residual = [&](int u, uint8_t* stg) {
-      bool ok = u < total_units;
-      int t_nt = 0, t_mt = 0;
-      if (ok) {
-        t_nt = u % p.n_tiles_n;
-        t_mt = (u / p.n_tiles_n) * CG + cta_rank;
-        ok = t_mt < p.n_tiles_m && t_nt * BN + c0 < p.Cout;
-      }
-      if (ok) {
-        const int t_tx = t_mt % p.tiles_x;
-        t_mt /= p.tiles_x;
-        const int t_ty = t_mt % p.tiles_y;
-        const int t_img = t_mt / p.tiles_y;
-        const int yy0 = t_ty * p.TH + ((q * 32) >> p.log2_tw), xx0 = t_tx * p.TW + ((q * 32) & (p.TW - 1));
-        const long long pix0 = (static_cast<long long>(t_img) * p.Ho + yy0) * p.Wo + xx0;
-        const __half* base = p.res + t_nt * BN + c0 + piece * 8;
+    auto issue_residual = [&](int u) {
+      if (u >= total_units) return;
+      const int t_nt = u % p.n_tiles_n;
+      int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
+      if (t_mt >= p.n_tiles_m || t_nt * BN + c0 >= p.Cout) return;
+      const int t_tx = t_mt % p.tiles_x;
+      t_mt /= p.tiles_x;
+      const int t_ty = t_mt % p.tiles_y;
+      const int t_img = t_mt / p.tiles_y;
+      const int yy0 = t_ty * p.TH + ((q * 32) >> p.log2_tw), xx0 = t_tx * p.TW + ((q * 32) & (p.TW - 1));
+      const long long pix0 = (static_cast<long long>(t_img) * p.Ho + yy0) * p.Wo + xx0;
+      const __half* base = p.res + t_nt * BN + c0 + piece * 8;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = (lane >> 2) + 8 * i;
-          const int dy = rr >> p.log2_tw, dx = rr & (p.TW - 1);
-          if (yy0 + dy < p.Ho && xx0 + dx < p.Wo) {      // rows outside the image are clipped by the TMA store: leave garbage
-            const __half* src = base + (pix0 + dy * p.Wo + dx) * p.Cout;
-            uint8_t* dst = stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4);
-            cp_async_16(dst, src);
-            cp_async_16(dst + 2048, src + p.res_plane);
-          }
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        const int dy = rr >> p.log2_tw, dx = rr & (p.TW - 1);
+        if (yy0 + dy < p.Ho && xx0 + dx < p.Wo) {      // rows outside the image are clipped by the TMA store: leave garbage
+          const __half* src = base + (pix0 + dy * p.Wo + dx) * p.Cout;
+          uint8_t* dst = stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4);
+          cp_async_16(dst, src);
+          cp_async_16(dst + 2048, src + p.res_plane);
         }
       }
       cp_async_commit();
     };
-    if (has_res) issue_residual(unit_first, stg_pair);
-    int acc = 0, buf = 0;
+    if (has_res) issue_residual(unit_first);
+    int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = unit_first; unit < total_units; unit += unit_stride) {
       const int nt = unit % p.n_tiles_n;
@@ -341,24 +331,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int img = mt / p.tiles_y;
       const int n0 = nt * BN;
       const bool chunk_ok = n0 + c0 < p.Cout;
-      uint8_t* stg = stg_pair + buf * 4096;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 2 * BN) + c0;
-      uint32_t a[16], b[16];
-      if (chunk_ok) {
-        tmem_ld_32x16(taddr, a);
-        tmem_ld_32x16(taddr + BN, b);
-      }
-      // the other staging tile: the previous tile's stores have been read out of it by now (they were issued a whole
-      // tile of work ago; the wait is a formality) -> refill it with the NEXT tile's residual while this tile is processed
-      if (lane == 0) tma_store_wait_read();
-      __syncwarp();
-      if (has_res) {
-        issue_residual(unit + unit_stride, stg_pair + (buf ^ 1) * 4096);
-        cp_async_wait_but_one();                                  // this tile's residual chunk has landed
-        __syncwarp();
-      }
       uint8_t* my_hi = stg + lane * 64;
       uint8_t* my_lo = my_hi + 2048;
       constexpr uint16_t kOneH = 0x3C00, kMinusOneH = 0xBC00;
@@ -405,6 +380,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       };
       if (chunk_ok) {
+        uint32_t a[16], b[16];
+        tmem_ld_32x16(taddr, a);
+        tmem_ld_32x16(taddr + BN, b);
+        if (has_res) { cp_async_wait_all(); __syncwarp(); }      // this tile's residual chunk is in the staging tile
         tmem_ld_wait();
         process16(a, b, 0);
         tmem_ld_32x16(taddr + 16, a);
@@ -424,7 +403,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int box_x = tx * p.TW + (r0 & (p.TW - 1)), box_y = ty * p.TH + (r0 >> p.log2_tw);
           tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
           tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
-          tma_store_commit();                                     // drains while the next tile is processed in the other staging tile
+          tma_store_commit();
+          tma_store_wait_read();                                  // staging tile drained: safe to refill
         }
         __syncwarp();
       } else {
@@ -435,11 +415,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      buf ^= 1;
+      if (has_res) issue_residual(unit + unit_stride);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (has_res) cp_async_wait_all();
     if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)

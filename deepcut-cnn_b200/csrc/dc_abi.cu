@@ -760,6 +760,21 @@ int dc_head_finish(const float* col, long long ldcol, int col_off, const float* 
   return DC_OK;
 }
 
+int dc_images_u8_to_blob(const unsigned char* img, int n, int h, int w, const float* mean3, float* out, void* stream) {
+  if (int rc = ensure_init()) return rc;
+  if (!img || !out || !mean3 || n <= 0 || h <= 0 || w <= 0) return fail(DC_ERR_INVALID, "dc_images_u8_to_blob: bad arguments");
+  const long long pixels = static_cast<long long>(n) * h * w;
+  const long long hw = static_cast<long long>(h) * w;
+  if (hw > 0x7FFFFFFF) return fail(DC_ERR_UNSUPPORTED, "dc_images_u8_to_blob: image too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(img) % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  if (vec) dc::images_u8_to_blob_kernel<<<ew_grid(pixels / 4), 256, 0, st>>>(img, out, pixels / 4, static_cast<int>(hw), mean3[0], mean3[1], mean3[2]);
+  else dc::images_u8_to_blob_scalar_kernel<<<ew_grid(pixels), 256, 0, st>>>(img, out, pixels, static_cast<int>(hw), mean3[0], mean3[1], mean3[2]);
+  g_launches++;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
 int dc_pose_from_maps(const float* prob, const float* loc, int n, int joints, int h, int w, float stride,
                       float locref_scale, float scale, float* out, void* stream) {
   if (int rc = ensure_init()) return rc;

@@ -477,4 +477,42 @@ __global__ void __launch_bounds__(256) preprocess_finish_kernel(const unsigned c
   out[2 * plane + o] = v2;
 }
 
+// ---------------------------------------------------------------------------------------
+// Batch of uint8 images [n][h][w][3] (what a decoder hands over; 3 B/pixel over PCIe / NVLink instead of the 12 B/pixel of the
+// float net input) -> the `data` blob, fp32 [n][3][h][w], minus the per-channel mean (estimate_pose.py:25,99).
+// Byte work, HBM-bound: each thread converts 4 adjacent pixels = 12 bytes in (three aligned 32-bit loads when w % 4 == 0),
+// three coalesced float4 stores out.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) images_u8_to_blob_kernel(const unsigned char* __restrict__ img, float* __restrict__ out,
+                                                                 long long quads, int hw, float m0, float m1, float m2) {
+  // quads = n * h * w / 4 (w % 4 == 0); a quad never straddles images because h*w % 4 == 0
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < quads; q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long px = q * 4;
+    const long long n = px / hw;
+    const int o = static_cast<int>(px - n * hw);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(img + px * 3);
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    // bytes: c0 c1 c2 | c0 c1 c2 | c0 c1 c2 | c0 c1 c2
+    const float4 p0 = make_float4((w0 & 0xFF) - m0, ((w0 >> 24) & 0xFF) - m0, ((w1 >> 16) & 0xFF) - m0, ((w2 >> 8) & 0xFF) - m0);
+    const float4 p1 = make_float4(((w0 >> 8) & 0xFF) - m1, (w1 & 0xFF) - m1, ((w1 >> 24) & 0xFF) - m1, ((w2 >> 16) & 0xFF) - m1);
+    const float4 p2 = make_float4(((w0 >> 16) & 0xFF) - m2, ((w1 >> 8) & 0xFF) - m2, (w2 & 0xFF) - m2, ((w2 >> 24) & 0xFF) - m2);
+    float* dst = out + n * 3 * static_cast<long long>(hw) + o;
+    *reinterpret_cast<float4*>(dst) = p0;
+    *reinterpret_cast<float4*>(dst + hw) = p1;
+    *reinterpret_cast<float4*>(dst + 2 * static_cast<long long>(hw)) = p2;
+  }
+}
+__global__ void __launch_bounds__(256) images_u8_to_blob_scalar_kernel(const unsigned char* __restrict__ img, float* __restrict__ out,
+                                                                        long long pixels, int hw, float m0, float m1, float m2) {
+  for (long long px = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; px < pixels; px += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = px / hw;
+    const long long o = px - n * hw;
+    const unsigned char* s = img + px * 3;
+    float* dst = out + n * 3 * static_cast<long long>(hw) + o;
+    dst[0] = static_cast<float>(s[0]) - m0;
+    dst[hw] = static_cast<float>(s[1]) - m1;
+    dst[2 * static_cast<long long>(hw)] = static_cast<float>(s[2]) - m2;
+  }
+}
+
 }  // namespace dc

@@ -120,3 +120,98 @@ class BatchExchange(object):
             if self.rank == 0:
                 self.out_host[k].copy_(g, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+
+
+class PipelinedExchange(object):
+    """The north_star's multi-GPU data path: rank 0 owns the whole host batch; every step it is uploaded once, NCCL-scattered
+    over NVLink into every rank, run through Net::Forward there, and the outputs the caller reads (`prob`, `loc_pred`) are
+    NCCL-gathered back to rank 0 and copied to its pinned host memory.  (The reference has no multi-GPU inference at all:
+    python/pose/pose_demo.py:71-74 takes one --gpu.)
+
+    What travels is the decoded uint8 image (3 B/pixel; 8 x 16 x 720p = 354 MB per step through rank 0's one PCIe link instead
+    of 1.4 GB of float input); each rank turns its shard into the float `data` blob on the device (dc_images_u8_to_blob).
+
+    Two streams per rank: the exchange stream (torch side stream; NCCL ops, rank 0's H2D / D2H) and Caffe's forward stream.
+    Step k+1's upload + scatter are queued BEFORE step k's forward, so they overlap it; step k's gather waits for its forward
+    through an event and overlaps step k+1's.  Buffers are double-buffered by step parity; the collectives are issued in the
+    same order on every rank (scatter k+1, gather k).
+    """
+
+    def __init__(self, dist, rank, world, net, libdc_mod, shard_n, h, w, out_names, host_u8=None, mean3=(104.0, 117.0, 123.0)):
+        import ctypes as C
+        import torch
+        from caffe._caffe import lib as clib
+        self.dist, self.rank, self.world, self.net = dist, rank, world, net
+        self.n, self.h, self.w = shard_n, h, w
+        self.C, self.L, self.check = C, libdc_mod.lib(), libdc_mod.check
+        self.cs_ptr = clib.caffe_stream()
+        self.cs = torch.cuda.ExternalStream(self.cs_ptr)
+        self.xs = torch.cuda.Stream()
+        self.mean = (C.c_float * 3)(*mean3)
+        self.recv = [torch.empty((shard_n, h, w, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        self.out_names = list(out_names)
+        self.out_shapes = {k: tuple(net.blobs[k].shape) for k in self.out_names}
+        self.stage = [{k: torch.empty(self.out_shapes[k], dtype=torch.float32, device="cuda") for k in self.out_names} for _ in range(2)]
+        self.ev_scat = [torch.cuda.Event() for _ in range(2)]
+        self.ev_fwd = [torch.cuda.Event() for _ in range(2)]
+        self.ev_gath = [torch.cuda.Event() for _ in range(2)]
+        self.full = self.host = self.gathered = self.out_host = None
+        if rank == 0:
+            assert host_u8 is not None and tuple(host_u8.shape) == (world * shard_n, h, w, 3) and host_u8.dtype == np.uint8
+            self.host = torch.from_numpy(host_u8).pin_memory()
+            self.full = [torch.empty_like(self.host, device="cuda") for _ in range(2)]
+            self.gathered = {k: torch.empty((world,) + self.out_shapes[k], dtype=torch.float32, device="cuda") for k in self.out_names}
+            self.out_host = {k: torch.empty((world * self.out_shapes[k][0],) + self.out_shapes[k][1:], dtype=torch.float32).pin_memory()
+                             for k in self.out_names}
+        self.h2d_bytes = world * shard_n * h * w * 3
+        self.d2h_bytes = sum(int(np.prod(s)) * 4 * world for s in self.out_shapes.values())
+        self.nvlink_bytes = (world - 1) * (shard_n * h * w * 3 + sum(int(np.prod(s)) * 4 for s in self.out_shapes.values()))
+
+    def submit_scatter(self, k):
+        import torch
+        b = k & 1
+        with torch.cuda.stream(self.xs):
+            # recv[b] was read by step k-2's conversion kernel: its forward finished before gather k-2, queued earlier on xs
+            chunks = None
+            if self.rank == 0:
+                self.full[b].copy_(self.host, non_blocking=True)
+                chunks = list(self.full[b].chunk(self.world, dim=0))
+            self.dist.scatter(self.recv[b], chunks, src=0)
+            self.ev_scat[b].record(self.xs)
+
+    def forward(self, k):
+        import torch
+        b = k & 1
+        self.cs.wait_event(self.ev_scat[b])
+        self.cs.wait_event(self.ev_gath[b])                 # stage[b] free again: step k-2's gather has read it
+        data = self.net.blobs["data"]
+        self.check(self.L.dc_images_u8_to_blob(self.C.c_void_p(self.recv[b].data_ptr()), self.n, self.h, self.w, self.mean,
+                                                self.C.c_void_p(data.overwrite_gpu_data_ptr()), self.C.c_void_p(self.cs_ptr)))
+        self.net.forward()
+        with torch.cuda.stream(self.cs):
+            for name in self.out_names:
+                self.stage[b][name].copy_(blob_tensor(self.net.blobs[name], mutable=False), non_blocking=True)
+            self.ev_fwd[b].record(self.cs)
+
+    def submit_gather(self, k):
+        import torch
+        b = k & 1
+        with torch.cuda.stream(self.xs):
+            self.xs.wait_event(self.ev_fwd[b])
+            for name in self.out_names:
+                dst = list(self.gathered[name].unbind(0)) if self.rank == 0 else None
+                self.dist.gather(self.stage[b][name], dst, dst=0)
+                if self.rank == 0:
+                    self.out_host[name].copy_(self.gathered[name].view(self.out_host[name].shape), non_blocking=True)
+            self.ev_gath[b].record(self.xs)
+
+    def run(self, steps):
+        """`steps` pipelined steps; returns when rank 0's pinned host buffers hold the last step's outputs."""
+        self.submit_scatter(0)
+        for k in range(steps):
+            if k + 1 < steps:
+                self.submit_scatter(k + 1)
+            self.forward(k)
+            self.submit_gather(k)
+        self.xs.synchronize()
+        self.cs.synchronize()

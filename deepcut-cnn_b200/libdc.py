@@ -38,6 +38,7 @@ _SIGS = {
     "dc_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dc_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "dc_event_sync": (C.c_int, [C.c_void_p]),
+    "dc_images_u8_to_blob": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "dc_graph_begin": (C.c_int, [C.c_void_p]),
     "dc_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "dc_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),

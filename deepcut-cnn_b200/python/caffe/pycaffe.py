@@ -81,6 +81,10 @@ class Blob(object):
         """Blob::mutable_gpu_data(): the device copy becomes the authoritative one (syncedmem.cpp:125-129)."""
         return check_ptr(lib.caffe_blob_mutable_gpu_data(self._h))
 
+    def overwrite_gpu_data_ptr(self):
+        """Device pointer for a writer of EVERY element (SyncedMemory::overwrite_gpu_data): no upload of a host copy first."""
+        return check_ptr(lib.caffe_blob_overwrite_gpu_data(self._h))
+
     def cpu_data_ptr(self):
         """Blob::cpu_data() (const): syncs a device-side head to the host, does NOT count as a host write."""
         return check_ptr(lib.caffe_blob_cpu_data(self._h))
@@ -96,7 +100,35 @@ class Blob(object):
         return self.HEADS[h]
 
 
-class _BlobArray(np.ndarray):
+def _loose(i):
+    """NumPy <= 1.11 index semantics the reference demo relies on (estimate_pose.py:167,251-255: cut_off = rf / stride is the
+    FLOAT 28.0 and is used as a slice bound): integral floats index like their int."""
+    if isinstance(i, (float, np.floating)) and float(i).is_integer():
+        return int(i)
+    if isinstance(i, slice):
+        return slice(_loose(i.start), _loose(i.stop), _loose(i.step))
+    if isinstance(i, tuple):
+        return tuple(_loose(j) for j in i)
+    return i
+
+
+class _LooseIndexArray(np.ndarray):
+    """ndarray that accepts integral floats as indices and keeps doing so through copy / transpose / np.concatenate ..., i.e.
+    for every array the demo derives from a ``Blob.data`` view."""
+    def __getitem__(self, idx):
+        return np.ndarray.__getitem__(self, _loose(idx))
+
+    def __setitem__(self, idx, value):
+        np.ndarray.__setitem__(self, _loose(idx), value)
+
+    def __array_function__(self, func, types, args, kwargs):
+        res = super().__array_function__(func, types, args, kwargs)
+        if type(res) is np.ndarray:
+            res = res.view(_LooseIndexArray)
+        return res
+
+
+class _BlobArray(_LooseIndexArray):
     """ndarray view that keeps its Blob (hence the C++ shared_ptr) alive."""
     def __new__(cls, arr, blob):
         obj = arr.view(cls)
@@ -156,6 +188,7 @@ class Net(object):
             raise TypeError("Net(network_file, [weights_file,] phase)")
         with open(network_file):          # same failure mode as CheckFile (_caffe.cpp:45-52)
             pass
+        self._network_file = network_file
         self._h = check_ptr(lib.caffe_net_create(network_file.encode(), int(phase)))
         if weights is not None:
             with open(weights):
@@ -301,6 +334,21 @@ class Net(object):
     @property
     def weight_bytes(self):
         return lib.caffe_net_weight_bytes(self._h)
+
+    def set_debug_info(self, on):
+        """NetParameter.debug_info: forwards run layer by layer and record mean|x| of every top blob (net.cpp:648-735)."""
+        check(lib.caffe_net_set_debug_info(self._h, int(bool(on))))
+
+    def debug_info(self):
+        """[(layer, top blob, mean|x|)] of the last forward run with set_debug_info(True)."""
+        cap = 8 * max(1, len(self._layer_names))
+        names = C.create_string_buffer(1 << 20)
+        vals = (C.c_double * cap)()
+        n = lib.caffe_net_debug_info(self._h, names, len(names), vals, cap)
+        if n < 0:
+            raise CaffeError(lib.caffe_last_error().decode(errors="replace"))
+        rows = names.value.decode().split("\n")[:n]
+        return [tuple(r.split(" ")) + (vals[i],) for i, r in enumerate(rows)]
 
     def describe_plan(self):
         """The fused execution plan for the current input shapes (steps, L2-resident segments, launch groups, arena),

@@ -11,10 +11,15 @@ import numpy as np
 MEAN_BGR = (104.0, 117.0, 123.0)   # python/pose/estimate_pose.py:25
 
 
+def images_u8(n, h, w, seed=20160505):
+    """The decoded images themselves: uint8 [n][h][w][3] (what images() subtracts the mean from)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+
+
 def images(n, h, w, seed=20160505):
     """uint8 image -> float32 NCHW minus the demo's per-channel mean."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    u8 = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    u8 = images_u8(n, h, w, seed)
     x = u8.astype(np.float32) - np.asarray(MEAN_BGR, np.float32)
     return np.ascontiguousarray(x.transpose(0, 3, 1, 2))
 

@@ -73,6 +73,11 @@ int caffe_net_set_step_timing(void* net, int on);
 int caffe_net_num_steps(void* net);
 int caffe_net_step_info(void* net, char* names, int names_cap, double* ms, double* flops, double* bytes, int max_steps);
 long long caffe_net_arena_bytes(void* net);
+/* NetParameter.debug_info (net.cpp:648-735): a forward with it on runs layer by layer and records mean|x| of every top blob
+ * (the reference only logs them).  caffe_net_debug_info copies the last forward's records: names = "layer blob\n" per record;
+ * returns the record count or -1. */
+int caffe_net_set_debug_info(void* net, int on);
+int caffe_net_debug_info(void* net, char* names, int names_cap, double* mean_abs, int max_records);
 /* 1 when blob i holds the value of the last forward; 0 for an intermediate the fused plan did not write (the reference fills
  * every blob each forward, net.cpp:565-581 -- the shim raises instead of returning stale data). */
 int caffe_net_blob_fresh(void* net, int i);

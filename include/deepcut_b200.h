@@ -195,6 +195,11 @@ int dc_preprocess_plan_info(const dc_preprocess_plan* plan, int* out_h, int* out
 int dc_preprocess_u8_forward(const dc_preprocess_plan* plan, const unsigned char* img, const float* mean3, float* out,
                              void* workspace, void* stream);
 int dc_preprocess_plan_destroy(dc_preprocess_plan* plan);
+/* A batch of decoded images into the net's input blob: img uint8 [n][h][w][3] (device) -> out fp32 [n][3][h][w] minus
+ * mean3[channel] -- the demo's `image.astype('float32') - _MEAN` + HWC->CHW (estimate_pose.py:99,225-227) without its rescale
+ * (dc_preprocess_u8_forward covers that).  What the multi-GPU batch exchange ships: 3 B/pixel instead of 12.  mean3 is read on
+ * the host. */
+int dc_images_u8_to_blob(const unsigned char* img, int n, int h, int w, const float* mean3, float* out, void* stream);
 /* Blob materialisation: fp32 NCHW <-> split NHWC. */
 int dc_nchw_to_split(const float* x, int n, int c, int h, int w, void* out, void* stream);
 int dc_split_to_nchw(const void* x, int n, int c, int h, int w, float* out, void* stream);
