@@ -970,6 +970,10 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
     return static_cast<char*>(t->ptr) + static_cast<size_t>(i0) * (t->elems() / t->n) * 2;
   };
   size_t issue_index = 0;
+  size_t conv_index = 0;
+  const bool serp = EnvOn("DC_SERPENTINE", false);
+  const int hints = getenv("DC_L2_HINTS") ? atoi(getenv("DC_L2_HINTS")) : 0;      // bit 0 evict_first for streams, 1 weights evict_last, 2 small outputs evict_last
+  const size_t small = EnvMiB("DC_L2_HINT_MB", 64u << 20);
   for (const Issue& is : schedule_) {
     Step* st = steps_[is.step];
     if (step_timing_) DC_CHECK(dc_event_record(events_[issue_index], stream));
@@ -1002,6 +1006,24 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
         a.stride = conv ? st->stride : 1;
         a.splitk_workspace = splitk_ws_;
         a.splitk_workspace_bytes = splitk_ws_bytes_;
+        if (conv) {
+          // Experiments (off by default; profiles/r2_chunk_sweep.md): DC_SERPENTINE=1 reverses the tile order of every other
+          // conv launch; DC_L2_HINTS tags operands with L2 eviction priorities -- tensors that fit L2 next to their consumer's
+          // other operands (<= DC_L2_HINT_MB, default 64) are written evict_last, larger ones streamed evict_first.
+          if (serp) a.reverse_units = static_cast<int>(conv_index & 1);
+          auto bytes_of = [&](const Tensor* t) { return t ? static_cast<size_t>(a.n) * (t->elems() / t->n) * 4 : 0; };
+          if (hints) {
+            const bool evict_first_on = (hints & 1) != 0, weights_on = (hints & 2) != 0, out_last_on = (hints & 4) != 0;
+            int h = 0;
+            if (evict_first_on && bytes_of(st->in) > small) h |= 1;
+            if (out_last_on && bytes_of(st->out) <= small) h |= 2 << 2;
+            else if (evict_first_on && bytes_of(st->out) > small) h |= 1 << 2;
+            if (evict_first_on && st->in2 && bytes_of(st->in2) > small) h |= 1 << 4;
+            if (weights_on) h |= 2 << 6;
+            a.l2_hints = h;
+          }
+          ++conv_index;
+        }
         DC_CHECK(dc_conv_forward(&a, stream));
         break;
       }

@@ -180,6 +180,7 @@ Dtype Net<Dtype>::ForwardFromTo(int start, int end) {
   CHECK_GE(start, 0);
   CHECK_LT(end, (int)layers_.size());
   Dtype loss = 0;
+  fused_last_forward_ = false;
   if (debug_info_) debug_log_.clear();
   for (int i = start; i <= end; ++i) {
     // a per-layer (partial) forward after a fused one: its bottoms must be values the last forward really left in the blobs

@@ -63,6 +63,10 @@ struct ConvParams {
   int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
   int in_stride;            // spatial stride of a 1x1 conv (the A map traverses W and H with this element stride); >= 1
   int early_weights;        // request the first stages' weight tiles before the grid dependency resolves (DC_EARLY_WEIGHTS)
+  int reverse;              // walk the work units from the last to the first: a layer that starts where its producer just finished
+                            // finds the most recently written part of its input still in L2 (serpentine schedule, dc_engine.cpp)
+  int l2_hints;             // L2 eviction priorities, 2 bits each (0 normal, 1 evict_first, 2 evict_last): [1:0] activations in,
+                            // [3:2] output, [5:4] residual, [7:6] weights
   float* sk_ws;             // split-K scratch: [unit][peer - 1][BN columns][128 rows] fp32 partial tiles (global memory, L2-resident)
 };
 
@@ -162,22 +166,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      const uint64_t pol_a = l2_policy(p.l2_hints & 3), pol_w = l2_policy((p.l2_hints >> 6) & 3);
       // Weights do not depend on the predecessor kernel: the weight tiles of this CTA's first K-steps (one per pipeline
       // stage) are requested BEFORE griddepcontrol.wait, so their HBM latency (a single image re-reads all 251 MB of
       // packed weights from HBM every forward) overlaps the predecessor's tail; the activation tiles follow after the wait.
       int npre = 0;
       if (p.early_weights && unit_first < total_units) {
-        const int n0 = (unit_first % p.n_tiles_n) * BN + cta_rank * Cfg::kBRows;
+        const int n0 = ((p.reverse ? total_units - 1 - unit_first : unit_first) % p.n_tiles_n) * BN + cta_rank * Cfg::kBRows;
         for (int ks = ks_begin; ks < ks_end && npre < kStages; ++ks, ++npre) {
           uint8_t* sa = smem + npre * Cfg::kStageBytes;
           if (CG == 2) {
             if (cta_rank == 0) mbar_expect_tx(&full_bar[npre], 2 * Cfg::kStageBytes);
-            tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0);
-            tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1);
+            tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
+            tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
           } else {
             mbar_expect_tx(&full_bar[npre], Cfg::kStageBytes);
-            tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0);
-            tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1);
+            tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
+            tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
           }
         }
       }
@@ -185,7 +190,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;
-      for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+      for (int it = unit_first; it < total_units; it += unit_stride) {
+        const int unit = p.reverse ? total_units - 1 - it : it;
         const int nt = unit % p.n_tiles_n;
         int mt = (unit / p.n_tiles_n) * CG + cta_rank;    // a phantom tile (mt == n_tiles_m) decodes to img == N: all-OOB boxes
         const int tx = mt % p.tiles_x;
@@ -205,19 +211,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (CG == 2) {
               // both CTAs' loads count on the leader's barrier; only the leader arms it (for both halves)
               if (cta_rank == 0 && fresh) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
-              tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
+              tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
+              tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
               if (fresh) {
-                tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
-                tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+                tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
+                tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
               }
             } else {
               if (fresh) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
-              tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
+              tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
+              tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
               if (fresh) {
-                tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0);
-                tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1);
+                tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
+                tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
               }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -294,8 +300,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int piece = lane & 3;
     const int own_sw = (lane >> 1) & 3;
     const bool has_res = p.res != nullptr;
-    auto issue_residual = [&](int u) {
-      if (u >= total_units) return;
+    const uint64_t pol_o = l2_policy((p.l2_hints >> 2) & 3), pol_r = l2_policy((p.l2_hints >> 4) & 3);
+    auto issue_residual = [&](int it_) {
+      if (it_ >= total_units) return;
+      const int u = p.reverse ? total_units - 1 - it_ : it_;
       const int t_nt = u % p.n_tiles_n;
       int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
       if (t_mt >= p.n_tiles_m || t_nt * BN + c0 >= p.Cout) return;
@@ -313,8 +321,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (yy0 + dy < p.Ho && xx0 + dx < p.Wo) {      // rows outside the image are clipped by the TMA store: leave garbage
           const __half* src = base + (pix0 + dy * p.Wo + dx) * p.Cout;
           uint8_t* dst = stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4);
-          cp_async_16(dst, src);
-          cp_async_16(dst + 2048, src + p.res_plane);
+          cp_async_16(dst, src, pol_r);
+          cp_async_16(dst + 2048, src + p.res_plane, pol_r);
         }
       }
       cp_async_commit();
@@ -322,7 +330,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (has_res) issue_residual(unit_first);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+    for (int it = unit_first; it < total_units; it += unit_stride) {
+      const int unit = p.reverse ? total_units - 1 - it : it;
       const int nt = unit % p.n_tiles_n;
       int mt = (unit / p.n_tiles_n) * CG + cta_rank;
       const int tx = mt % p.tiles_x;
@@ -401,8 +410,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
           const int r0 = q * 32;
           const int box_x = tx * p.TW + (r0 & (p.TW - 1)), box_y = ty * p.TH + (r0 >> p.log2_tw);
-          tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
-          tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
+          tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0, pol_o);
+          tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1, pol_o);
           tma_store_commit();
           tma_store_wait_read();                                  // staging tile drained: safe to refill
         }
@@ -415,7 +424,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      if (has_res) issue_residual(unit + unit_stride);
+      if (has_res) issue_residual(it + unit_stride);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -426,12 +435,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;       // which of the two warps of this quarter
     const int row = q * 32 + lane;          // accumulator row (TMEM lane) this thread owns
+    const uint64_t pol_o = l2_policy((p.l2_hints >> 2) & 3);
     // residual prefetch registers (split-NHWC mode): 4 rows x {hi, lo} x 16 B of the NEXT chunk
     uint4 res_h[4], res_l[4];
-    auto prefetch_residual = [&](int u, int c0) {
+    auto prefetch_residual = [&](int it_, int c0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0); }
-      if (u >= total_units) return;
+      if (it_ >= total_units) return;
+      const int u = p.reverse ? total_units - 1 - it_ : it_;
       const int t_nt = u % p.n_tiles_n;
       int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
       if (t_mt >= p.n_tiles_m) return;
@@ -478,7 +489,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+    for (int it = unit_first; it < total_units; it += unit_stride) {
+      const int unit = (SK == 0 && p.reverse) ? total_units - 1 - it : it;     // split-K launches (one unit per cluster) never reverse
       const int nt = unit % p.n_tiles_n;
       int mt = (unit / p.n_tiles_n) * CG + cta_rank;
       const bool tile_ok = mt < p.n_tiles_m;       // the odd CTA of the last pair may own a phantom tile
@@ -562,7 +574,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (n0 + c0 >= p.Cout) {
             // ragged last channel tile: nothing to do here, but if this was the warp's first chunk the
             // prefetch registers still hold the zeros meant for it -- refill them for the next tile
-            if (p.res != nullptr && c0 == half * 32) prefetch_residual(unit + unit_stride, half * 32);
+            if (p.res != nullptr && c0 == half * 32) prefetch_residual(it + unit_stride, half * 32);
             break;
           }
           uint32_t r[32], rx[32];
@@ -580,8 +592,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             __syncwarp();
             // prefetch the residual of the chunk this warp handles next (same tile, or the next tile's first)
-            int nunit = unit, nc0 = c0 + 64;
-            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { nunit = unit + unit_stride; nc0 = half * 32; }
+            int nunit = it, nc0 = c0 + 64;
+            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { nunit = it + unit_stride; nc0 = half * 32; }
             prefetch_residual(nunit, nc0);
           }
           float sc[32], sh[32];
@@ -633,8 +645,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0) {
-            tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
-            tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
+            tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0, pol_o);
+            tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1, pol_o);
             tma_store_commit();
           }
         }

@@ -600,6 +600,8 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.out_mode = a->out_f32_rows == 2 ? dc::kOutF32RowsT : (a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC);
   p.swap_ab = a->out_f32_rows == 2;
   p.early_weights = use_early_weights();
+  p.reverse = a->reverse_units ? 1 : 0;
+  p.l2_hints = a->l2_hints & 0xFF;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
 
   CUtensorMap ta, tb, to;

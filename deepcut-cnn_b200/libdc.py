@@ -13,7 +13,8 @@ class ConvArgs(C.Structure):
                 ("w_packed", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
                 ("relu", C.c_int), ("out_f32_rows", C.c_int), ("ldc", C.c_int), ("out", C.c_void_p), ("stride", C.c_int),
                 ("splitk_workspace", C.c_void_p), ("splitk_workspace_bytes", C.c_size_t),
-                ("x_plane", C.c_longlong), ("out_plane", C.c_longlong), ("residual_plane", C.c_longlong)]
+                ("x_plane", C.c_longlong), ("out_plane", C.c_longlong), ("residual_plane", C.c_longlong),
+                ("reverse_units", C.c_int), ("l2_hints", C.c_int)]
 
 
 _SIGS = {

@@ -29,8 +29,9 @@ def main():
                 if k in d:
                     print("| %s | %s %s |" % (k, d[k][1], d[k][0]))
             try:
-                tr = float(d["dram__bytes_read.sum"][1]) + float(d["dram__bytes_write.sum"][1])
-                print("| traffic = dram read + write | %.1f %s |" % (tr, d["dram__bytes_read.sum"][0]))
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tr = sum(float(d[k][1]) * mult[d[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                print("| traffic = dram read + write | %.1f Mbyte |" % (tr / 1e6))
             except (KeyError, ValueError):
                 pass
 
