@@ -971,8 +971,11 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
   };
   size_t issue_index = 0;
   size_t conv_index = 0;
-  const bool serp = EnvOn("DC_SERPENTINE", false);
-  const int hints = getenv("DC_L2_HINTS") ? atoi(getenv("DC_L2_HINTS")) : 0;      // bit 0 evict_first for streams, 1 weights evict_last, 2 small outputs evict_last
+  const bool serp = EnvOn("DC_SERPENTINE", false), merge_2a = EnvOn("DC_MERGE_ACC_2A", false);
+  // bit 0: evict_first for streamed activations, bit 1: weights evict_last, bit 2: small outputs evict_last.  Default = weights
+  // only: the one hint that measured a gain (res4's 3x3 convs 7.5 -> 7.1 ms per 16x720p step: every CTA re-reads the layer's
+  // 2.4 MB of packed weights for each tile while 100+ MB of activations stream through L2; profiles/r2_chunk_sweep.md)
+  const int hints = getenv("DC_L2_HINTS") ? atoi(getenv("DC_L2_HINTS")) : 2;
   const size_t small = EnvMiB("DC_L2_HINT_MB", 64u << 20);
   for (const Issue& is : schedule_) {
     Step* st = steps_[is.step];
@@ -1011,6 +1014,8 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
           // conv launch; DC_L2_HINTS tags operands with L2 eviction priorities -- tensors that fit L2 next to their consumer's
           // other operands (<= DC_L2_HINT_MB, default 64) are written evict_last, larger ones streamed evict_first.
           if (serp) a.reverse_units = static_cast<int>(conv_index & 1);
+          // DC_MERGE_ACC_2A=1 (experiment): the 1x1 reduce convs (no shortcut) accumulate all three products in one accumulator
+          if (merge_2a && st->kh == 1 && !st->in2 && st->relu) a.merge_accumulators = 1;
           auto bytes_of = [&](const Tensor* t) { return t ? static_cast<size_t>(a.n) * (t->elems() / t->n) * 4 : 0; };
           if (hints) {
             const bool evict_first_on = (hints & 1) != 0, weights_on = (hints & 2) != 0, out_last_on = (hints & 4) != 0;

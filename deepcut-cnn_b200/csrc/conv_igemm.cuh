@@ -63,6 +63,8 @@ struct ConvParams {
   int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
   int in_stride;            // spatial stride of a 1x1 conv (the A map traverses W and H with this element stride); >= 1
   int early_weights;        // request the first stages' weight tiles before the grid dependency resolves (DC_EARLY_WEIGHTS)
+  int merge_acc;            // experiment: all three products into ONE accumulator (no separate cross terms): what BN = 256 tiles would
+                            // need to keep double-buffered accumulators in 512 TMEM columns; costs RZ-accumulation bias
   int reverse;              // walk the work units from the last to the first: a layer that starts where its producer just finished
                             // finds the most recently written part of its input still in L2 (serpentine schedule, dc_engine.cpp)
   int l2_hints;             // L2 eviction priorities, 2 bits each (0 normal, 1 evict_first, 2 evict_last): [1:0] activations in,
@@ -244,7 +246,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 2 * BN);   // main
-        const uint32_t dx = d + BN;                                            // cross terms
+        const uint32_t dx = p.merge_acc ? d : d + BN;                          // cross terms
         uint32_t accum = 0;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
           mbar_wait(&full_bar[stage], phase);
@@ -260,7 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // hi*hi, hi*lo and lo*hi are symmetric in (A, B): swapping the operands only transposes D
             if (CG == 2) {
               umma_f16_2cta(d, a_hi + adv, b_hi + adv, idesc, accum);
-              umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, accum);
+              umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, p.merge_acc ? 1u : accum);
               accum = 1;
               umma_f16_2cta(dx, a_lo + adv, b_hi + adv, idesc, 1);
             } else if (p.swap_ab) {
@@ -605,6 +607,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             sh[4 * g] = b4.x; sh[4 * g + 1] = b4.y; sh[4 * g + 2] = b4.z; sh[4 * g + 3] = b4.w;
           }
           tmem_ld_wait();
+          if (p.merge_acc) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rx[j] = 0u;
+          }
           if constexpr (SK != 0) add_partials(r, rx, c0);
           float v[32];
 #pragma unroll

@@ -635,6 +635,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (ksplit > 1) return bn == 128 ? launch_conv<128, 1, 8, 1>(ta, tb, to, p, st, ksplit) : launch_conv<64, 1, 8, 1>(ta, tb, to, p, st, ksplit);
   // epilogue-bound layers (short K, wide output: the 1x1 expand convs) get the 16-warp lean epilogue
+  p.merge_acc = (a->merge_accumulators && pair && !(pair && lean_shape) && p.out_mode == dc::kOutSplitNHWC) ? 1 : 0;
   const bool lean = pair && lean_shape;
   if (lean) return launch_conv<128, 2, 16>(ta, tb, to, p, st);
   if (bn == 128) return pair ? launch_conv<128, 2>(ta, tb, to, p, st) : launch_conv<128, 1>(ta, tb, to, p, st);

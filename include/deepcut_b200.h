@@ -132,6 +132,7 @@ typedef struct dc_conv_args {
    * operand (0 normal, 1 evict_first, 2 evict_last): bits [1:0] x, [3:2] out, [5:4] residual, [7:6] weights. */
   int reverse_units;
   int l2_hints;
+  int merge_accumulators;    /* experiment (CTA-pair kernels with split output only): hi*hi, hi*lo and lo*hi into one TMEM accumulator */
 } dc_conv_args;
 /* Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-24) =
  * im2col_gpu (util/im2col.cu:8-62) + cublasSgemm (util/math_functions.cu:13-27) per image, and the

@@ -23,7 +23,7 @@ def _gpu():
         pytest.skip("needs a CUDA device")
 
 
-PARITY_JSON = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_margins.json")
+PARITY_JSON = os.environ.get("DC_PARITY_JSON") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_margins.json")
 
 
 def _report(tag, got, ref, record=False):
