@@ -85,10 +85,15 @@ struct ConvCfg {
   static constexpr int kBRows = BN / CG;                 // B rows resident in THIS CTA
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static_assert(BN == 64 || BN == 128, "4 accumulators of BN columns must fit 512 TMEM columns");
+  static_assert(BN == 64 || BN == 128 || (BN == 256 && CG == 2 && EW == 8), "BN = 256: CTA pairs with the 8-warp epilogue only");
+  // TMEM holds kAccBufs (main, cross) accumulator pairs of BN columns each: two for BN <= 128 (the epilogue of tile i overlaps the
+  // MMAs of tile i+1), ONE for BN = 256 (all 512 columns).  BN = 256 exists for the long-K 1x1 reduce convs, which are bound by
+  // operand bytes arriving per SM (conv_igemm's header): one A tile against 256 channels needs 64 KB per 2 x 768 MMA cycles
+  // (42 B/clk) instead of 48 KB per 768 (62.5 B/clk), which buys more than the un-overlapped epilogue costs when K >= 512.
+  static constexpr int kAccBufs = BN == 256 ? 1 : 2;
   static_assert(EW == 8 || (EW == 16 && BN == 128), "the 16-warp epilogue owns one 32-channel chunk per warp: BN = 128");
-  static constexpr int kStages = (CG == 2 ? 4 : (BN >= 128 ? 3 : 4)) - (EW == 16 ? 1 : 0);
-  static constexpr int kTmemCols = 4 * BN;                         // 2 x (main, cross)
+  static constexpr int kStages = BN == 256 ? 3 : (CG == 2 ? 4 : (BN >= 128 ? 3 : 4)) - (EW == 16 ? 1 : 0);
+  static constexpr int kTmemCols = 2 * BN * kAccBufs;              // kAccBufs x (main, cross)
   static constexpr int kStagingBytes = EW * 4096;        // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo}
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -283,8 +288,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (CG == 2) umma_commit_2cta(&tfull_bar[acc]);
         else umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == Cfg::kAccBufs) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (EW == 16) {
@@ -427,8 +431,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       if (has_res) issue_residual(it + unit_stride);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == Cfg::kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();
   } else {
@@ -688,8 +691,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
         else mbar_arrive(&tempty_bar[acc]);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == Cfg::kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();     // bulk stores must complete before the CTA's shared memory goes away
   }

@@ -303,6 +303,7 @@ int dc_init(int device) {
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 2, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2, 16>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<256, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<256, 2, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 1, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 1, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::kC1SmemFloats * 4));
@@ -631,6 +632,14 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
           static_cast<size_t>(units) * (s - 1) * bn * 128 * 4 <= a->splitk_workspace_bytes) { ksplit = s; break; }
   }
   const bool pair = ksplit == 1 && use_2cta() && !p.swap_ab && g_num_sms >= 2 && (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)));
+  // 256-channel tiles for the long-K 1x1 reduce convs (res4 / res5 branch2a): one activation tile against 256 output channels,
+  // 2/3 of the operand bytes per MMA; single-buffered accumulators, so only where the K loop (>= 8 K-steps) dwarfs the
+  // epilogue and the launch still fills the SMs.  Same per-element K chains as the 128-channel tiles: bitwise the same output.
+  // DC_CONV_BN256=0 disables.
+  static const bool bn256_on = [] { const char* e = getenv("DC_CONV_BN256"); return !(e && e[0] == '0'); }();
+  const bool wide256 = bn256_on && pair && !lean_shape && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res == nullptr && rows % 256 == 0 &&
+                       p.ntaps * (a->cin / dc::kBK) >= 8 && static_cast<long long>((p.n_tiles_m + 1) / 2) * (rows / 256) * 2 >= g_num_sms;
+  if (wide256) { bn = 256; p.n_tiles_n = rows / 256; }
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair ? bn / 2 : bn)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (ksplit > 1) return bn == 128 ? launch_conv<128, 1, 8, 1>(ta, tb, to, p, st, ksplit) : launch_conv<64, 1, 8, 1>(ta, tb, to, p, st, ksplit);
@@ -638,6 +647,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.merge_acc = (a->merge_accumulators && pair && !(pair && lean_shape) && p.out_mode == dc::kOutSplitNHWC) ? 1 : 0;
   const bool lean = pair && lean_shape;
   if (lean) return launch_conv<128, 2, 16>(ta, tb, to, p, st);
+  if (wide256) return launch_conv<256, 2, 8>(ta, tb, to, p, st);
   if (bn == 128) return pair ? launch_conv<128, 2>(ta, tb, to, p, st) : launch_conv<128, 1>(ta, tb, to, p, st);
   return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
 }

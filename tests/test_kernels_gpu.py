@@ -46,6 +46,10 @@ CONV_CASES = [
     (128, 128, 1, 0, 1, 120, 160, 1),
     (64, 128, 1, 0, 1, 132, 192, 1),
     (64, 192, 3, 1, 1, 40, 48, 5),
+    # long-K 1x1 reduce convs with enough pixels for the 256-channel-tile CTA-pair kernel (conv_igemm<256, 2, 8>, single-buffered
+    # accumulators): res4 branch2a (one 256-channel tile) and res5 branch2a (two), 45x80 maps with a ragged last pixel tile
+    (1024, 256, 1, 0, 1, 45, 80, 6),
+    (2048, 512, 1, 0, 1, 45, 83, 3),
 ]
 
 
