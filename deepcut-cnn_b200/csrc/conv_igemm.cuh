@@ -63,6 +63,9 @@ struct ConvParams {
   int swap_ab;              // BN == 128 only: D[weight row][pixel] instead of D[pixel][channel]
   int in_stride;            // spatial stride of a 1x1 conv (the A map traverses W and H with this element stride); >= 1
   int early_weights;        // request the first stages' weight tiles before the grid dependency resolves (DC_EARLY_WEIGHTS)
+  int debug_skip;           // MICROBENCHMARK ONLY (wrong results): after the first pipeline fill the producer stops loading the weight
+                            // tiles (bit 0) / the activation tiles (bit 1); the MMAs run on whatever the stages hold.  Gives the time a
+                            // weight-resident / activation-resident variant of a layer could reach before building it (DC_DEBUG_SKIP)
   int merge_acc;            // experiment: all three products into ONE accumulator (no separate cross terms): what BN = 256 tiles would
                             // need to keep double-buffered accumulators in 512 TMEM columns; costs RZ-accumulation bias
   int reverse;              // walk the work units from the last to the first: a layer that starts where its producer just finished
@@ -214,6 +217,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             const int kcoord = (t * kchunks + kc) * kBK;
             const bool fresh = issued >= npre;      // else: this stage's barrier is armed and its weight tiles are on their way
+            if (p.debug_skip && issued >= kStages) {
+              // microbenchmark mode: arm the barrier for exactly what is still loaded
+              const bool ld_a = !(p.debug_skip & 2), ld_b = !(p.debug_skip & 1);
+              const uint32_t bytes = (ld_a ? 2u * Cfg::kABytes : 0u) + (ld_b ? 2u * Cfg::kBBytes : 0u);
+              ++issued;
+              if (CG == 2) {
+                if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);
+                if (ld_a) {
+                  tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
+                  tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
+                }
+                if (ld_b) {
+                  tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
+                  tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
+                }
+              } else {
+                mbar_expect_tx(&full_bar[stage], bytes);
+                if (ld_a) {
+                  tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
+                  tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
+                }
+                if (ld_b) {
+                  tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
+                  tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
+                }
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             ++issued;
             if (CG == 2) {
               // both CTAs' loads count on the leader's barrier; only the leader arms it (for both halves)

@@ -601,6 +601,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.out_mode = a->out_f32_rows == 2 ? dc::kOutF32RowsT : (a->out_f32_rows ? dc::kOutF32Rows : dc::kOutSplitNHWC);
   p.swap_ab = a->out_f32_rows == 2;
   p.early_weights = use_early_weights();
+  { const char* e = getenv("DC_DEBUG_SKIP"); p.debug_skip = e ? (atoi(e) & 3) : 0; }      // microbenchmarks only: results are wrong
   p.reverse = a->reverse_units ? 1 : 0;
   p.l2_hints = a->l2_hints & 0xFF;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
@@ -637,8 +638,17 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   // epilogue and the launch still fills the SMs.  Same per-element K chains as the 128-channel tiles: bitwise the same output.
   // DC_CONV_BN256=0 disables.
   static const bool bn256_on = [] { const char* e = getenv("DC_CONV_BN256"); return !(e && e[0] == '0'); }();
-  const bool wide256 = bn256_on && pair && !lean_shape && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res == nullptr && rows % 256 == 0 &&
-                       p.ntaps * (a->cin / dc::kBK) >= 8 && static_cast<long long>((p.n_tiles_m + 1) / 2) * (rows / 256) * 2 >= g_num_sms;
+  // Measured (profiles/r2_ncu_summary.md): a 256-channel unit costs ~1.8x a 128-channel one (-7..10 % per unit of work), so the wider
+  // tile only wins when it does not cost a wave: res5 branch2a at 16x720p (450 units on 74 CTA pairs: 7 rounds x 1.8 < 13) takes it,
+  // res4 branch2a (225 units = 3.04 waves -> 4 rounds x 1.8 > 7) does not.
+  bool wide256 = bn256_on && pair && !lean_shape && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res == nullptr && rows % 256 == 0 &&
+                 p.ntaps * (a->cin / dc::kBK) >= 8;
+  if (wide256) {
+    const long long pairs = g_num_sms / 2, mp = (p.n_tiles_m + 1) / 2;
+    const long long rounds128 = (mp * (rows / 128) + pairs - 1) / pairs, rounds256 = (mp * (rows / 256) + pairs - 1) / pairs;
+    static const bool force = [] { const char* e = getenv("DC_CONV_BN256"); return e && e[0] == '2'; }();      // 2 = wherever legal (A/B runs)
+    wide256 = force ? mp * (rows / 256) >= pairs : (rounds256 * 18 < rounds128 * 10 && mp * (rows / 256) >= pairs);
+  }
   if (wide256) { bn = 256; p.n_tiles_n = rows / 256; }
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair ? bn / 2 : bn)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

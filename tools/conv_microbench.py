@@ -128,6 +128,19 @@ if __name__ == "__main__":
         run_latency(1, 32, 32, 2048, 512, 1, 0, 1, 0)
         run_latency(1, 64, 64, 128, 128, 3, 1, 1, 0)
         run_latency(1, 64, 64, 512, 128, 1, 0, 1, 0)
+    elif args.set == "bound":
+        # what bounds the 1x1 convs: the same launches with the weight tiles (DC_DEBUG_SKIP=1), the activation tiles (2) or both (3)
+        # no longer loaded after the first pipeline fill (results are garbage; only the time counts), and without the residual
+        for skip in ("0", "1", "2", "3"):
+            os.environ["DC_DEBUG_SKIP"] = skip
+            print("--- DC_DEBUG_SKIP=%s (1: no weight-tile loads, 2: no activation-tile loads)" % skip)
+            run(16, 45, 80, 256, 1024, 1, 0, 1, 1, 0)        # res4 2c + shortcut
+            run(16, 45, 80, 256, 1024, 1, 0, 1, 0, 0)        # ... without the residual stream
+            run(16, 45, 80, 1024, 256, 1, 0, 1, 0, 0)        # res4 2a
+            run(16, 45, 80, 256, 256, 3, 1, 1, 0, 0)         # res4 2b
+            run(16, 90, 160, 128, 512, 1, 0, 1, 1, 0)        # res3 2c
+            run(16, 180, 320, 64, 256, 1, 0, 1, 1, 0)        # res2 2c
+        os.environ.pop("DC_DEBUG_SKIP")
     elif args.set == "c3":
         run(16, 180, 320, 64, 64, 3, 1, 1, 0, 0)
         run(16, 90, 160, 128, 128, 3, 1, 1, 0, 0)
