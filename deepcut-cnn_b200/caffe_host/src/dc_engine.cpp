@@ -517,8 +517,8 @@ void FusedPlan::PlanSchedule() {
   for (Tensor* t : tensors_) { t->alloc_step = t->def_step; t->free_step = t->last_step; }
 
   // Off by default: measured on B200 (profiles/r2_chunk_sweep.md) the chunked schedule cuts a forward's DRAM traffic from 74.6 GB
-  // to 32.8 GB, yet the step gets SLOWER -- these convs are bound by per-SM operand latency and wave quantisation, not by HBM,
-  // and a sub-batch launch has 3-16x fewer tiles to hide either.
+  // to 32.8 GB, yet the step gets SLOWER -- operand delivery is already hidden behind the MMAs (profiles/r2_microbench_bound.txt), so
+  // fewer DRAM bytes buy nothing, while a sub-batch launch has 3-16x fewer tiles per wave and pays ramp + tail as many times more often.
   const size_t budget = EnvMiB("DC_L2_CHUNK_MB", 0);
   std::vector<int> forced;
   if (const char* e = getenv("DC_CHUNK_PLAN")) {

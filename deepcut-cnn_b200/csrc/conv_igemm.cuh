@@ -90,9 +90,10 @@ struct ConvCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static_assert(BN == 64 || BN == 128 || (BN == 256 && CG == 2 && EW == 8), "BN = 256: CTA pairs with the 8-warp epilogue only");
   // TMEM holds kAccBufs (main, cross) accumulator pairs of BN columns each: two for BN <= 128 (the epilogue of tile i overlaps the
-  // MMAs of tile i+1), ONE for BN = 256 (all 512 columns).  BN = 256 exists for the long-K 1x1 reduce convs, which are bound by
-  // operand bytes arriving per SM (conv_igemm's header): one A tile against 256 channels needs 64 KB per 2 x 768 MMA cycles
-  // (42 B/clk) instead of 48 KB per 768 (62.5 B/clk), which buys more than the un-overlapped epilogue costs when K >= 512.
+  // MMAs of tile i+1), ONE for BN = 256 (all 512 columns).  BN = 256 exists for the long-K 1x1 reduce convs: one A tile against 256
+  // channels (64 KB per 2 x 768 MMA cycles instead of 48 KB per 768, half as many MMA issues per FLOP) measured ~7 % faster per unit
+  // of work than two 128-channel tiles despite the un-overlapped epilogue -- and only pays where halving the unit count does not
+  // cost a wave (dc_conv_forward decides; profiles/r2_ncu_summary.md).
   static constexpr int kAccBufs = BN == 256 ? 1 : 2;
   static_assert(EW == 8 || (EW == 16 && BN == 128), "the 16-warp epilogue owns one 32-channel chunk per warp: BN = 128");
   static constexpr int kStages = BN == 256 ? 3 : (CG == 2 ? 4 : (BN >= 128 ? 3 : 4)) - (EW == 16 ? 1 : 0);
@@ -327,8 +328,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ lean epilogue (warps 2..17), split-NHWC only
     // (Round 2 tried two staging tiles per warp -- the residual of tile i+1 streaming in while tile i is converted -- paid for
     // with one operand stage (227 KB of shared memory hold 3 x 48 KB stages + 64 KB of staging, or 2 + 128): 112.7 -> 132.6 us
-    // on res4's 2c.  The sampled stalls moved from the epilogue to the MMA issuer waiting on `full` barriers: these K <= 512
-    // layers are bound by operand bytes in flight per SM, not by the epilogue chain; profiles/r2_ncu_summary.md.)
+    // on res4's 2c: with two stages the mainloop starves and the faster epilogue only waits longer on `tmem_full`.  For this shape
+    // shared memory holds three operand stages or a double-buffered epilogue, not both; profiles/r2_ncu_summary.md.)
     // One 32-pixel x 32-channel chunk per warp per tile.  The residual chunk is copied global -> staging by
     // cp.async as soon as the previous tile's TMA stores have drained the staging tile, i.e. while the
     // next accumulator is still being computed; accumulators are read 16 columns at a time.
