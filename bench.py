@@ -68,6 +68,10 @@ def parse_args():
     ap.add_argument("--e2e-inflight", type=int, default=2,
                     help="end-to-end leg: requests in flight (Net instances on their own host thread + stream); 1 = strictly serial")
     ap.add_argument("--step-report", default=None, help="write the per-step roofline table to this path")
+    ap.add_argument("--only-exchange", action="store_true",
+                    help="tuning aid (N > 1): skip the per-rank e2e leg, the roofline pass, the latency point and the CPU baseline")
+    ap.add_argument("--exchange-reserved-sms", type=int, default=int(os.environ.get("DC_EXCHANGE_RESERVED_SMS", "8")),
+                    help="SMs the forwards leave to NCCL's kernels while the batch exchange is in flight (dc_set_reserved_sms)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0,
                     help="--impl reference: host seconds the (warmup + steps) samples may take; a step shrinks from one image to its top 1/d")
     return ap.parse_args()
@@ -354,7 +358,9 @@ def main():
         prob.data                       # D2H + sync (what estimate_pose.py reads)
         loc.data
     e2e_mode = "serial"
-    if args.e2e_inflight > 1:
+    if args.only_exchange:
+        e2e_wall_ms = 0.0
+    elif args.e2e_inflight > 1:
         # Double-buffered serving through the same public API: a second Net (own host thread, own stream, own arena;
         # weights packed from the same blobs) keeps the GPU busy while the first one's H2D / D2H copies are in flight.
         import threading
@@ -416,7 +422,7 @@ def main():
         for _ in range(2):
             e2e_step()
         _, e2e_wall_ms = timed(e2e_step, args.steps)
-    e2e_value = world * B * args.steps / (e2e_wall_ms / 1e3)     # host wall clock: includes every copy and sync
+    e2e_value = world * B * args.steps / (e2e_wall_ms / 1e3) if e2e_wall_ms > 0 else None     # host wall clock: includes every copy and sync
 
     # ---- N > 1: the batch exchange the north_star names -- rank 0 owns the WHOLE host batch (uint8 images), NCCL scatter over
     # NVLink into every rank's `data` blob, forward, NCCL gather of prob + loc_pred back to rank 0's pinned host memory;
@@ -425,6 +431,11 @@ def main():
     if dist is not None:
         dmod = importlib.import_module("deepcut-cnn_b200.dist")
         host_u8 = synth.images_u8(world * B, H, W, seed=20160505) if rank == 0 else None
+        # the forwards leave a few SMs to NCCL's copy kernels (persistent one-CTA-per-SM grids cannot share theirs): new grid size ->
+        # drop the plan so that the CUDA graph is captured again
+        libdc.check(L.dc_set_reserved_sms(args.exchange_reserved_sms))
+        net.materialize_intermediates(True)
+        net.materialize_intermediates(False)
         ex = dmod.PipelinedExchange(dist, rank, world, net, libdc, B, H, W, ["prob", "loc_pred"], host_u8=host_u8)
         ex.run(3)
         barrier()
@@ -439,13 +450,18 @@ def main():
                         "nvlink_bytes_per_step": int(ex.nvlink_bytes), "steps": args.steps,
                         "mode": "rank 0 owns the global host batch (uint8 HWC): H2D on rank 0, NCCL scatter, on-device u8->float, "
                                 "forward, NCCL gather of prob+loc_pred to rank 0, D2H; scatter k+1 / gather k overlap forward k"}
+        exchange_rec["reserved_sms"] = int(L.dc_get_reserved_sms())
+        exchange_rec["nccl_env"] = {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}
         if exchange:
             e2e_value, e2e_wall_ms, h2d, d2h, e2e_mode = exchange_rec["value"], ex_wall_ms, ex.h2d_bytes, ex.d2h_bytes, exchange_rec["mode"]
         del ex
+        libdc.check(L.dc_set_reserved_sms(0))
+        net.materialize_intermediates(True)
+        net.materialize_intermediates(False)
     # ---- per-step roofline pass (separate from the timed region: events around every step)
     roofline = None
     report = None
-    if rank == 0:
+    if rank == 0 and not args.only_exchange:
         pk = peaks()
         net.set_step_timing(True)
         for _ in range(4):               # back to back, so the table is taken at sustained (power-capped) clocks
@@ -463,17 +479,25 @@ def main():
                     "share_of_step": cms / total_ms, "launches": len(conv), "peak_source": pk["source"], "traffic": None}
         # the launch the tensor-pipe target is judged on (dilated res5 3x3): live per-launch numbers + the committed ncu traffic
         rep = [s_ for s_ in info if s_[1].startswith("res5b_branch2b")]
-        tr_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        # `traffic` = DRAM bytes of that launch from the COMMITTED ncu launch list (profiles/r2_traffic.json: one profiled forward of this
+        # workload, --cache-control none); it is not measured in this run -- `traffic_source` says so -- and only given for the workload it
+        # was captured on.  r1's --set full capture supplies the tensor-pipe reading.
+        tr_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if rep and rep[0][2] > 0:
             r_ach = rep[0][3] / (rep[0][2] / 1e3) / 1e12
             roofline["representative"] = {"launch": rep[0][1], "ms": rep[0][2], "achieved": r_ach, "frac": r_ach / pk["tflops"],
                                           "issued_frac": 3 * r_ach / pk["tflops"], "algorithmic_bytes": rep[0][4]}
-            if os.path.exists(tr_path) and (B, H, W) == (16, 720, 1280):
-                tr = json.load(open(tr_path))["launches"].get("res5b_branch2b")
+            if os.path.exists(tr_path) and (B, H, W) == (16, 720, 1280) and args.model == "152":
+                doc = json.load(open(tr_path))
+                tr = doc["launches"].get("res5b_branch2b")
                 if tr:
                     roofline["traffic"] = tr["dram_bytes"]
+                    roofline["traffic_source"] = "committed ncu capture, not measured in this run: profiles/r2_traffic.json (" + doc["source"].split(",")[0] + " ...)"
                     roofline["representative"]["traffic"] = tr["dram_bytes"]
-                    roofline["representative"]["tensor_pipe_active_pct_ncu"] = tr["tensor_pipe_active_pct"]
+                    roofline["forward_dram_bytes_ncu"] = doc.get("forward_dram_bytes")
+                r1 = os.path.join(ROOT, "profiles", "r1_traffic.json")
+                if os.path.exists(r1):
+                    roofline["representative"]["tensor_pipe_active_pct_ncu"] = json.load(open(r1))["launches"]["res5b_branch2b"]["tensor_pipe_active_pct"]
         report = {"total_ms": total_ms, "steps": [{"type": s[0], "name": s[1], "ms": s[2], "gflop": s[3] / 1e9, "mbytes": s[4] / 1e6,
                                                     "tflops": (s[3] / (s[2] / 1e3) / 1e12) if s[2] > 0 else 0.0,
                                                     "gbs": (s[4] / (s[2] / 1e3) / 1e9) if s[2] > 0 else 0.0} for s in info]}
@@ -503,7 +527,7 @@ def main():
 
     # ---- CPU baseline (oracle/_ref = the reference's CPU layers; numpy port if absent), rank 0 at N = 1 only
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.only_exchange:
         dt, cpu_baseline, _, _ = time_cpu_reference(path, x[:1], 1, 3, budget_s=40.0)    # 1 warm-up + 3 timed, ~10-30 s of CPU work
         cpu_baseline["value"] = 1.0 / dt
 

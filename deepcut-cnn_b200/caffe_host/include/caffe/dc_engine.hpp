@@ -37,7 +37,10 @@ class PlanWeightCache {
   size_t bytes = 0;
 
  private:
-  std::vector<std::pair<SyncedMemory*, unsigned long long> > epochs_;
+  // (parameter blob, the SyncedMemory it had when the weights were packed, that memory's write epoch): holding the shared_ptr keeps
+  // the comparison valid when a blob is reshaped or re-pointed (ShareData) afterwards
+  struct Seen { const Blob<float>* blob; std::shared_ptr<SyncedMemory> mem; unsigned long long epoch; };
+  std::vector<Seen> epochs_;
 };
 
 class FusedPlan {

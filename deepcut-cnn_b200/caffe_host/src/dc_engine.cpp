@@ -421,8 +421,8 @@ PlanWeightCache::~PlanWeightCache() {
   for (void* p : allocs) dc_free(p);
 }
 bool PlanWeightCache::Stale() const {
-  for (const auto& we : epochs_)
-    if (we.first->host_write_epoch() != we.second) return true;
+  for (const Seen& we : epochs_)
+    if (we.blob->data() != we.mem || we.mem->host_write_epoch() != we.epoch) return true;
   return false;
 }
 void PlanWeightCache::Snapshot(Net<float>& net) {
@@ -430,7 +430,8 @@ void PlanWeightCache::Snapshot(Net<float>& net) {
   for (const auto& layer : net.layers())
     for (const auto& blob : layer->blobs()) {
       blob->cpu_data();     // make sure the SyncedMemory exists and is host-readable
-      epochs_.push_back(std::make_pair(blob->data().get(), blob->data()->host_write_epoch()));
+      Seen seen = {blob.get(), blob->data(), blob->data()->host_write_epoch()};
+      epochs_.push_back(seen);
     }
 }
 

@@ -216,8 +216,26 @@ bool Message::ParseText(TextLexer& lx, char closer) {
     if (lx.Peek().kind == Token::PUNCT && lx.Peek().text == ":") lx.Take();
     const int rc = TextField(name, lx);
     if (rc == 1) {
-      if (!SkipValue(lx)) { lx.error = "line " + std::to_string(t.line) + ": cannot skip unknown field '" + name + "'"; return false; }
-      fprintf(stderr, "proto_lite: %s has no field '%s' in this build (line %d) -- skipped\n", TypeName(), name.c_str(), t.line);
+      // protobuf's TextFormat (the reference's ReadProtoFromTextFile, io.cpp:34-44) rejects a field the schema does not have: a
+      // misspelt parameter must not silently yield a different net.  The only names skipped are the caffe.proto fields this build
+      // deliberately does not model -- parameters of layer types outside the forward path (their layers are refused by the registry
+      // anyway) and the training-only propagate_down.
+      static const char* const kOutOfScope[] = {
+          "propagate_down", "transform_param", "loss_param", "accuracy_param", "argmax_param", "concat_param", "contrastive_loss_param",
+          "data_param", "dropout_param", "dummy_data_param", "elu_param", "embed_param", "exp_param", "flatten_param", "hdf5_data_param",
+          "hdf5_output_param", "hinge_loss_param", "image_data_param", "infogain_loss_param", "inner_product_param", "log_param", "lrn_param",
+          "memory_data_param", "mvn_param", "power_param", "prelu_param", "python_param", "reduction_param", "reshape_param", "softmax_param",
+          "spp_param", "slice_param", "tanh_param", "threshold_param", "tile_param", "window_data_param", "pose_data_param",
+          "softmax_with_loss_vec_param"};
+      bool skippable = false;
+      if (std::string(TypeName()) == "LayerParameter")
+        for (const char* k : kOutOfScope) skippable = skippable || name == k;
+      if (!skippable) {
+        lx.error = "line " + std::to_string(t.line) + ": message " + TypeName() + " has no field named '" + name + "'";
+        return false;
+      }
+      if (!SkipValue(lx)) { lx.error = "line " + std::to_string(t.line) + ": cannot skip field '" + name + "'"; return false; }
+      fprintf(stderr, "proto_lite: LayerParameter.%s (line %d) belongs to a layer type outside the forward path -- skipped\n", name.c_str(), t.line);
     } else if (rc == 2) {
       if (lx.error.empty()) lx.error = "line " + std::to_string(t.line) + ": bad value for " + TypeName() + "." + name;
       return false;

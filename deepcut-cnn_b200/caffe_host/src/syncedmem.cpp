@@ -110,12 +110,14 @@ void SyncedMemory::set_gpu_data(void* data) {
   CHECK(data);
   if (own_gpu_data_ && gpu_ptr_) dc_free(gpu_ptr_);
   gpu_ptr_ = data;
+  ++host_epoch_;
   head_ = HEAD_AT_GPU;
   own_gpu_data_ = false;
 }
 
 void* SyncedMemory::mutable_cpu_data() { to_cpu(); wait_upload(); head_ = HEAD_AT_CPU; ++host_epoch_; return cpu_ptr_; }
-void* SyncedMemory::mutable_gpu_data() { to_gpu(); head_ = HEAD_AT_GPU; return gpu_ptr_; }
+// device-side writers count as writes too (a parameter blob updated through mutable_gpu_data must invalidate packed copies of it)
+void* SyncedMemory::mutable_gpu_data() { to_gpu(); head_ = HEAD_AT_GPU; ++host_epoch_; return gpu_ptr_; }
 
 void* SyncedMemory::overwrite_gpu_data() {
   if (gpu_ptr_ == nullptr) {

@@ -43,6 +43,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
+// SMs the persistent conv grids leave free (dc_set_reserved_sms): a persistent kernel with one CTA per SM and a static tile schedule
+// cannot share its SMs -- a concurrent NCCL kernel that takes even a few of them delays the CTAs that should have run there by a whole
+// kernel, i.e. doubles that kernel's time.  While a batch exchange is in flight the forwards therefore run on SMs - reserve.
+std::atomic<int> g_reserved_sms{[] { const char* e = getenv("DC_RESERVED_SMS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }()};
+int persistent_sms() {
+  const int n = g_num_sms - g_reserved_sms.load();
+  return n >= 2 ? n : 2;
+}
 // a layer's K loop is shared by a split-K cluster only from this many 64-channel K-steps on (DC_SPLIT_K_MIN_STEPS)
 std::atomic<int> g_split_k_min_steps{[] { const char* e = getenv("DC_SPLIT_K_MIN_STEPS"); const int v = e ? atoi(e) : 16; return v >= 8 ? v : 16; }()};
 bool g_inited = false;
@@ -175,7 +183,8 @@ template <int BN, int CG, int EW = 8, int SK = 0>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st,
                 int ksplit = 1) {
   const int units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
-  int grid = units * CG < g_num_sms ? units * CG : g_num_sms;
+  const int sms = persistent_sms();
+  int grid = units * CG < sms ? units * CG : sms;
   if (CG == 2) grid &= ~1;
   if (SK) grid = units * ksplit;
   cudaLaunchConfig_t cfg;
@@ -256,6 +265,12 @@ int dc_set_split_k(int max_split) {
   return DC_OK;
 }
 int dc_get_split_k(void) { return g_split_k_max.load(); }
+int dc_set_reserved_sms(int n) {
+  if (n < 0 || (g_num_sms > 0 && n > g_num_sms - 2)) return fail(DC_ERR_INVALID, "dc_set_reserved_sms: %d out of range", n);
+  g_reserved_sms.store(n);
+  return DC_OK;
+}
+int dc_get_reserved_sms(void) { return g_reserved_sms.load(); }
 size_t dc_splitk_workspace_bytes(void) {
   // units * S <= SMs and a slot is at most a 128 x 128 fp32 tile: units * (S - 1) slots < SMs slots
   return static_cast<size_t>(g_num_sms > 0 ? g_num_sms : 148) * 128 * 128 * 4;
@@ -644,7 +659,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   bool wide256 = bn256_on && pair && !lean_shape && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res == nullptr && rows % 256 == 0 &&
                  p.ntaps * (a->cin / dc::kBK) >= 8;
   if (wide256) {
-    const long long pairs = g_num_sms / 2, mp = (p.n_tiles_m + 1) / 2;
+    const long long pairs = persistent_sms() / 2, mp = (p.n_tiles_m + 1) / 2;
     const long long rounds128 = (mp * (rows / 128) + pairs - 1) / pairs, rounds256 = (mp * (rows / 256) + pairs - 1) / pairs;
     static const bool force = [] { const char* e = getenv("DC_CONV_BN256"); return e && e[0] == '2'; }();      // 2 = wherever legal (A/B runs)
     wide256 = force ? mp * (rows / 256) >= pairs : (rounds256 * 18 < rounds128 * 10 && mp * (rows / 256) >= pairs);

@@ -54,6 +54,8 @@ _SIGS = {
     "dc_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "dc_set_split_k": (C.c_int, [C.c_int]),
     "dc_get_split_k": (C.c_int, []),
+    "dc_set_reserved_sms": (C.c_int, [C.c_int]),
+    "dc_get_reserved_sms": (C.c_int, []),
     "dc_splitk_workspace_bytes": (C.c_size_t, []),
     "dc_set_split_k_min_steps": (C.c_int, [C.c_int]),
     "dc_get_split_k_min_steps": (C.c_int, []),

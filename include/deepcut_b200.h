@@ -150,6 +150,11 @@ int dc_conv_forward(const dc_conv_args* args, void* stream);
  * Process-wide; takes effect for launches (and CUDA-graph captures) made after the call. */
 int dc_set_split_k(int max_split);
 int dc_get_split_k(void);
+/* SMs the persistent convolution grids leave free for kernels running beside a forward (NCCL's, during a multi-GPU batch
+ * exchange): a persistent one-CTA-per-SM kernel with a static tile schedule cannot share an SM without stretching to twice its time.
+ * Process-wide; takes effect for launches (and CUDA-graph captures) made after the call.  Default 0 (env DC_RESERVED_SMS). */
+int dc_set_reserved_sms(int n);
+int dc_get_reserved_sms(void);
 /* Upper bound of the scratch any split launch needs on this device (SM count x one 128 x 128 fp32 tile). */
 size_t dc_splitk_workspace_bytes(void);
 /* A K loop is shared only from `min_ksteps` 64-channel K-steps on (taps * cin / 64; env DC_SPLIT_K_MIN_STEPS): the exchange

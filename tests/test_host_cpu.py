@@ -294,3 +294,21 @@ def test_shim_covers_every_caffe_name_the_reference_demo_uses():
     blob.data[0, ...] = np.ones((3, 40, 48), np.float32)          # :228
     assert blob.data.shape == (1, 3, 40, 48) and float(blob.data.sum()) == 3 * 40 * 48
     assert callable(net.forward) and "loc_pred" in net.blobs and "prob" in net.blobs      # :229-232
+
+
+def test_prototxt_rejects_unknown_fields_like_protobuf_textformat():
+    """ReadProtoFromTextFile (io.cpp:34-44) is protobuf TextFormat: a field the schema lacks is an error, not a note -- a
+    misspelt parameter must not silently build a different net.  Only caffe.proto fields of layer types outside the forward
+    path (and the training-only propagate_down) are skipped."""
+    caffe = dcutil.caffe_module()
+    caffe.set_mode_cpu()
+    head = 'name: "t" input: "data" input_dim: 1 input_dim: 3 input_dim: 8 input_dim: 8 '
+    bad = head + 'layer { name: "c" type: "Convolution" bottom: "data" top: "c" convolution_param { num_output: 4 kernel_size: 1 strde: 2 } }'
+    with pytest.raises(caffe._caffe.CaffeError, match="ConvolutionParameter has no field named 'strde'"):
+        caffe.Net.from_string(bad, caffe.TEST)
+    with pytest.raises(caffe._caffe.CaffeError, match="no field named 'inptu'"):
+        caffe.Net.from_string(head.replace('input: "data"', 'inptu: "data"'), caffe.TEST)
+    ok = head + ('layer { name: "c" type: "Convolution" bottom: "data" top: "c" propagate_down: false dropout_param { dropout_ratio: 0.5 } '
+                 'convolution_param { num_output: 4 kernel_size: 1 stride: 2 } }')
+    net = caffe.Net.from_string(ok, caffe.TEST)
+    assert net.blobs["c"].shape == (1, 4, 4, 4)
