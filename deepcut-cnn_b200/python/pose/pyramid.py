@@ -62,41 +62,60 @@ def work_items(shapes, scales):
     return items
 
 
+def _is_device(img):
+    return hasattr(img, "data_ptr")          # a torch CUDA uint8 tensor (what the NCCL broadcast leaves on every rank)
+
+
 def run_items(images, items, model_def, model_bin, weights=None):
-    """Runs (image index, scale) items on THIS rank's GPU; items of one input geometry share a forward.
+    """Runs (image index, scale) items on THIS rank's GPU; items of one input geometry share a forward.  `images[i]` is a uint8
+    HxWx3 numpy array (uploaded once, whatever the number of scales) or a CUDA tensor (used in place).
     -> float32 [len(items), 5, 14] poses in item order."""
     L = _libdc.lib()
     stream = C.c_void_p(_caffe._caffe.lib.caffe_stream())
     out = np.zeros((len(items), 5, 14), np.float32)
+    # every distinct image on the device once
+    need = sorted({i for i, _, _ in items})
+    host = [i for i in need if not _is_device(images[i])]
+    dev = {i: int(images[i].data_ptr()) for i in need if _is_device(images[i])}
+    keep = []
+    if host:
+        base = _buf("img", sum(int(np.prod(images[i].shape)) for i in host)).value
+        off = 0
+        for i in host:
+            img = np.ascontiguousarray(images[i], np.uint8)
+            keep.append(img)
+            _libdc.check(L.dc_memcpy_async(C.c_void_p(base + off), img.ctypes.data_as(C.c_void_p), img.nbytes, 1, stream))
+            dev[i] = base + off
+            off += img.nbytes
     groups = {}
     for k, (i, s, _) in enumerate(items):
         h, w = images[i].shape[:2]
-        groups.setdefault((h, w, s), []).append(k)
+        groups.setdefault((int(h), int(w), s), []).append(k)
     mean = _ep._MEAN.ctypes.data_as(C.POINTER(C.c_float))
+    pending = []
+    d_pose_all = _buf("pose", out.nbytes).value
     for (h, w, s), ks in groups.items():
         plan, out_h, out_w, ws = _ep._plan(h, w, s)
         n = len(ks)
         net = _net(model_def, model_bin, n, out_h, out_w, weights)
-        data = net.blobs["data"]
-        base = data.overwrite_gpu_data_ptr()
-        d_img = _buf("img", n * h * w * 3)
+        base = net.blobs["data"].overwrite_gpu_data_ptr()
         d_ws = _buf("ws", ws) if ws else None
         for slot, k in enumerate(ks):
-            img = np.ascontiguousarray(images[items[k][0]], np.uint8)
-            src = C.c_void_p(d_img.value + slot * h * w * 3)
-            _libdc.check(L.dc_memcpy_async(src, img.ctypes.data_as(C.c_void_p), img.nbytes, 1, stream))
-            _libdc.check(L.dc_preprocess_u8_forward(plan, src, mean, C.c_void_p(base + slot * 3 * out_h * out_w * 4), d_ws, stream))
-            _libdc.check(L.dc_stream_sync(stream))            # `img` may be a temporary: the copy must have read it
+            _libdc.check(L.dc_preprocess_u8_forward(plan, C.c_void_p(dev[items[k][0]]), mean, C.c_void_p(base + slot * 3 * out_h * out_w * 4), d_ws, stream))
         net.forward()
         prob, loc = net.blobs["prob"], net.blobs["loc_pred"]
-        poses = np.zeros((n, 5, 14), np.float32)
-        d_pose = _buf("pose", poses.nbytes)
+        d_pose = d_pose_all + len(pending) * 5 * 14 * 4
         _libdc.check(L.dc_pose_from_maps(prob.gpu_data_ptr(), loc.gpu_data_ptr(), n, 14, prob.shape[2], prob.shape[3], _ep._STRIDE,
-                                         _ep._LOCREF_SCALE_MUL, float(s), d_pose, stream))
-        _libdc.check(L.dc_memcpy_async(poses.ctypes.data_as(C.c_void_p), d_pose, poses.nbytes, 2, stream))
-        _libdc.check(L.dc_stream_sync(stream))
-        for slot, k in enumerate(ks):
-            out[k] = poses[slot]
+                                         _ep._LOCREF_SCALE_MUL, float(s), C.c_void_p(d_pose), stream))
+        pending += ks
+    # one read-back for all groups (stream-ordered behind every forward), one sync
+    got = np.zeros((len(pending), 5, 14), np.float32)
+    if len(pending):
+        _libdc.check(L.dc_memcpy_async(got.ctypes.data_as(C.c_void_p), C.c_void_p(d_pose_all), got.nbytes, 2, stream))
+    _libdc.check(L.dc_stream_sync(stream))
+    for slot, k in enumerate(pending):
+        out[k] = got[slot]
+    del keep
     return out
 
 
@@ -129,11 +148,11 @@ def estimate_poses_pyramid(images, model_def, model_bin, scales=(0.5, 1.0, 1.5),
         if rank == 0:
             flat.copy_(torch.from_numpy(np.concatenate([np.ascontiguousarray(im, np.uint8).ravel() for im in images])))
         dist.broadcast(flat, src=0)                                   # the batch scatter (22 MB for 8 x 720p)
-        host = flat.cpu().numpy()
+        torch.cuda.current_stream().synchronize()                     # NCCL ran on torch's stream; the forwards run on Caffe's
         images, off = [], 0
         for s in shapes:
             n = int(np.prod(s))
-            images.append(host[off:off + n].reshape(s))
+            images.append(flat[off:off + n].view(*s))                 # stays on the device: pre-processing reads it in place
             off += n
     items = work_items([im.shape[:2] for im in images], scales)
     bins = _dist.lpt_assign([c for _, _, c in items], world)
