@@ -39,6 +39,28 @@ constexpr int conv_threads(int ew) { return 64 + 32 * ew; }
 
 enum OutMode : int { kOutSplitNHWC = 0, kOutF32Rows = 1, kOutF32RowsT = 2 };
 
+// Division by a launch constant as multiply-high + shift (host: fastdiv_make).  The tile decode -- three div/mod pairs per work
+// unit, done by every epilogue warp twice per tile -- compiled to ~20 SASS instructions per division (I2F / MUFU.RCP / fix-up) and
+// made up a third of the lean epilogue's instruction stream (profiles/r2_ncu_summary.md); exact for 0 <= x < 2^31.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv fastdiv_make(int d) {
+  FastDiv f;
+  f.d = static_cast<uint32_t>(d > 0 ? d : 1);
+  if (f.d == 1) { f.mul = 0; f.shr = 0; return f; }
+  uint32_t lg = 0;
+  while ((1u << lg) < f.d) ++lg;                    // ceil(log2 d)
+  const uint32_t p = 31 + lg;
+  f.mul = static_cast<uint32_t>(((1ull << p) + f.d - 1) / f.d);
+  f.shr = p - 32;
+  return f;
+}
+__device__ __forceinline__ void fastdivmod(const FastDiv& f, int x, int& q, int& r) {
+  q = f.d == 1 ? x : static_cast<int>(__umulhi(static_cast<uint32_t>(x), f.mul) >> f.shr);
+  r = x - q * static_cast<int>(f.d);
+}
+
 struct ConvParams {
   int H, W;                 // input spatial dims as seen by the A tensor map
   int Ho, Wo, Cout;         // output geometry (Cout = real channel count)
@@ -51,6 +73,7 @@ struct ConvParams {
   int tiles_x, tiles_y;     // per image
   int n_tiles_m;            // N * tiles_y * tiles_x
   int n_tiles_n;            // ceil(Cout / BN)
+  FastDiv div_ntn, div_tx, div_ty;   // fast division by n_tiles_n, tiles_x, tiles_y
   const float* scale;       // [n_tiles_n * BN] per-channel multiplier (folded BN*Scale*weight pow2)
   const float* shift;       // [n_tiles_n * BN]
   const __half* res;        // residual (split NHWC, same geometry as the output) or nullptr
@@ -110,6 +133,18 @@ struct ConvCfg {
 // mbarrier in the leader's shared memory; the leader's epilogue waits on it (acquire, cluster scope), reads the slots
 // with L1-bypassing loads and sums own + slot 0 + slot 1 + ... in that fixed order (no atomics: repeated runs are bitwise
 // identical).  The grid is exactly units * S CTAs, so nothing is persistent in this mode.
+// work unit -> (n-tile, tile x, tile y, image); a phantom tile (m-tile == n_tiles_m, the odd CTA of the last pair) decodes to
+// image == N: all of its TMA boxes are out of bounds
+template <int CG>
+__device__ __forceinline__ void decode_unit(const ConvParams& p, int unit, int cta_rank, int& nt, int& mt, int& tx, int& ty, int& img) {
+  int mg;
+  fastdivmod(p.div_ntn, unit, mg, nt);
+  mt = mg * CG + cta_rank;
+  int rest;
+  fastdivmod(p.div_tx, mt, rest, tx);
+  fastdivmod(p.div_ty, rest, img, ty);
+}
+
 template <int BN, int CG, int EW, int SK = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -183,7 +218,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // packed weights from HBM every forward) overlaps the predecessor's tail; the activation tiles follow after the wait.
       int npre = 0;
       if (p.early_weights && unit_first < total_units) {
-        const int n0 = ((p.reverse ? total_units - 1 - unit_first : unit_first) % p.n_tiles_n) * BN + cta_rank * Cfg::kBRows;
+        int q0, nt0;
+        fastdivmod(p.div_ntn, p.reverse ? total_units - 1 - unit_first : unit_first, q0, nt0);
+        const int n0 = nt0 * BN + cta_rank * Cfg::kBRows;
         for (int ks = ks_begin; ks < ks_end && npre < kStages; ++ks, ++npre) {
           uint8_t* sa = smem + npre * Cfg::kStageBytes;
           if (CG == 2) {
@@ -203,12 +240,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int issued = 0;
       for (int it = unit_first; it < total_units; it += unit_stride) {
         const int unit = p.reverse ? total_units - 1 - it : it;
-        const int nt = unit % p.n_tiles_n;
-        int mt = (unit / p.n_tiles_n) * CG + cta_rank;    // a phantom tile (mt == n_tiles_m) decodes to img == N: all-OOB boxes
-        const int tx = mt % p.tiles_x;
-        mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int img = mt / p.tiles_y;
+        int nt, mt, tx, ty, img;
+        decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN + cta_rank * Cfg::kBRows;
         for (int t = 0; t < p.ntaps; ++t) {
           const int ix = x0 * p.in_stride + p.tap_dx[t], iy = y0 * p.in_stride + p.tap_dy[t];
@@ -343,13 +376,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     auto issue_residual = [&](int it_) {
       if (it_ >= total_units) return;
       const int u = p.reverse ? total_units - 1 - it_ : it_;
-      const int t_nt = u % p.n_tiles_n;
-      int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
+      int t_nt, t_mt, t_tx, t_ty, t_img;
+      decode_unit<CG>(p, u, cta_rank, t_nt, t_mt, t_tx, t_ty, t_img);
       if (t_mt >= p.n_tiles_m || t_nt * BN + c0 >= p.Cout) return;
-      const int t_tx = t_mt % p.tiles_x;
-      t_mt /= p.tiles_x;
-      const int t_ty = t_mt % p.tiles_y;
-      const int t_img = t_mt / p.tiles_y;
       const int yy0 = t_ty * p.TH + ((q * 32) >> p.log2_tw), xx0 = t_tx * p.TW + ((q * 32) & (p.TW - 1));
       const long long pix0 = (static_cast<long long>(t_img) * p.Ho + yy0) * p.Wo + xx0;
       const __half* base = p.res + t_nt * BN + c0 + piece * 8;
@@ -371,12 +400,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     for (int it = unit_first; it < total_units; it += unit_stride) {
       const int unit = p.reverse ? total_units - 1 - it : it;
-      const int nt = unit % p.n_tiles_n;
-      int mt = (unit / p.n_tiles_n) * CG + cta_rank;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
+      int nt, mt, tx, ty, img;
+      decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
       const int n0 = nt * BN;
       const bool chunk_ok = n0 + c0 < p.Cout;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -481,13 +506,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int i = 0; i < 4; ++i) { res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0); }
       if (it_ >= total_units) return;
       const int u = p.reverse ? total_units - 1 - it_ : it_;
-      const int t_nt = u % p.n_tiles_n;
-      int t_mt = (u / p.n_tiles_n) * CG + cta_rank;
+      int t_nt, t_mt, t_tx, t_ty, t_img;
+      decode_unit<CG>(p, u, cta_rank, t_nt, t_mt, t_tx, t_ty, t_img);
       if (t_mt >= p.n_tiles_m) return;
-      const int t_tx = t_mt % p.tiles_x;
-      t_mt /= p.tiles_x;
-      const int t_ty = t_mt % p.tiles_y;
-      const int t_img = t_mt / p.tiles_y;
       if (t_nt * BN + c0 >= p.Cout) return;
       // rows (lane >> 2) + 8 i of the warp's 32-row sub-rectangle (TW is a power of two: shifts, no divides)
       const int yy0 = t_ty * p.TH + ((q * 32) >> p.log2_tw), xx0 = t_tx * p.TW + ((q * 32) & (p.TW - 1));
@@ -529,13 +550,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     for (int it = unit_first; it < total_units; it += unit_stride) {
       const int unit = (SK == 0 && p.reverse) ? total_units - 1 - it : it;     // split-K launches (one unit per cluster) never reverse
-      const int nt = unit % p.n_tiles_n;
-      int mt = (unit / p.n_tiles_n) * CG + cta_rank;
+      int nt, mt, tx, ty, img;
+      decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
       const bool tile_ok = mt < p.n_tiles_m;       // the odd CTA of the last pair may own a phantom tile
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
       const int n0 = nt * BN;
 
       mbar_wait(&tfull_bar[acc], acc_phase);

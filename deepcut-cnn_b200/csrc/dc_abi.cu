@@ -183,6 +183,10 @@ template <int BN, int CG, int EW = 8, int SK = 0>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st,
                 int ksplit = 1) {
   const int units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
+  dc::ConvParams pk = p;                       // the launch's copy, with the tile-decode divisors filled in
+  pk.div_ntn = dc::fastdiv_make(p.n_tiles_n);
+  pk.div_tx = dc::fastdiv_make(p.tiles_x);
+  pk.div_ty = dc::fastdiv_make(p.tiles_y);
   const int sms = persistent_sms();
   int grid = units * CG < sms ? units * CG : sms;
   if (CG == 2) grid &= ~1;
@@ -209,7 +213,7 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG, EW, SK>, ta, tb, to, p));
+  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG, EW, SK>, ta, tb, to, pk));
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
@@ -619,6 +623,10 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   { const char* e = getenv("DC_DEBUG_SKIP"); p.debug_skip = e ? (atoi(e) & 3) : 0; }      // microbenchmarks only: results are wrong
   p.reverse = a->reverse_units ? 1 : 0;
   p.l2_hints = a->l2_hints & 0xFF;
+  // weights evict_last pays when every CTA re-reads the layer's weight tiles for many pixel tiles; a launch with fewer pixel tiles than
+  // SMs (a single image) reads each weight tile once, and 251 MB of evict_last lines per forward would only push the activations out
+  static const bool hint_small = [] { const char* e = getenv("DC_L2_HINTS_SMALL"); return e && e[0] == '1'; }();     // A/B switch
+  if (!hint_small && ((p.l2_hints >> 6) & 3) == 2 && p.n_tiles_m < g_num_sms) p.l2_hints &= ~0xC0;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
 
   CUtensorMap ta, tb, to;
