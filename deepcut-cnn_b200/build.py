@@ -31,7 +31,8 @@ def build_kernels(force=False):
     if not force and _newer(LIB_DC, srcs):
         return LIB_DC
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
-    _run([nvcc] + NVCC_FLAGS + ["-o", LIB_DC, os.path.join(csrc, "dc_abi.cu")])
+    extra = os.environ.get("DC_EXTRA_NVCC_FLAGS", "").split()        # A/B builds (e.g. -DDC_PTX_NO_CACHE_HINT)
+    _run([nvcc] + NVCC_FLAGS + extra + ["-o", LIB_DC, os.path.join(csrc, "dc_abi.cu")])
     return LIB_DC
 
 

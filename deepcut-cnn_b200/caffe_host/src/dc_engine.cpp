@@ -971,13 +971,11 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
     return static_cast<char*>(t->ptr) + static_cast<size_t>(i0) * (t->elems() / t->n) * 2;
   };
   size_t issue_index = 0;
-  size_t conv_index = 0;
-  const bool serp = EnvOn("DC_SERPENTINE", false), merge_2a = EnvOn("DC_MERGE_ACC_2A", false);
-  // bit 0: evict_first for streamed activations, bit 1: weights evict_last, bit 2: small outputs evict_last.  Default = weights
-  // only: the one hint that measured a gain (res4's 3x3 convs 7.5 -> 7.1 ms per 16x720p step: every CTA re-reads the layer's
-  // 2.4 MB of packed weights for each tile while 100+ MB of activations stream through L2; profiles/r2_chunk_sweep.md)
-  const int hints = getenv("DC_L2_HINTS") ? atoi(getenv("DC_L2_HINTS")) : 2;
-  const size_t small = EnvMiB("DC_L2_HINT_MB", 64u << 20);
+  // Weight tiles stay in L2 with the evict_last priority (DC_WEIGHTS_EVICT_LAST=0 disables): the one L2 hint of round 2's sweep that
+  // measured a gain (res4's 3x3 convs 7.5 -> 7.1 ms per 16x720p step).  evict_first on streamed activations, evict_last on small
+  // outputs, a serpentine tile order and merged accumulators were measured too and removed again: profiles/r2_chunk_sweep.md,
+  // tools/experiments/r2_removed_switches.patch.
+  const bool weights_last = EnvOn("DC_WEIGHTS_EVICT_LAST", true);
   for (const Issue& is : schedule_) {
     Step* st = steps_[is.step];
     if (step_timing_) DC_CHECK(dc_event_record(events_[issue_index], stream));
@@ -1010,26 +1008,7 @@ void FusedPlan::IssueSteps(const std::vector<const void*>& blob_ptrs, void* stre
         a.stride = conv ? st->stride : 1;
         a.splitk_workspace = splitk_ws_;
         a.splitk_workspace_bytes = splitk_ws_bytes_;
-        if (conv) {
-          // Experiments (off by default; profiles/r2_chunk_sweep.md): DC_SERPENTINE=1 reverses the tile order of every other
-          // conv launch; DC_L2_HINTS tags operands with L2 eviction priorities -- tensors that fit L2 next to their consumer's
-          // other operands (<= DC_L2_HINT_MB, default 64) are written evict_last, larger ones streamed evict_first.
-          if (serp) a.reverse_units = static_cast<int>(conv_index & 1);
-          // DC_MERGE_ACC_2A=1 (experiment): the 1x1 reduce convs (no shortcut) accumulate all three products in one accumulator
-          if (merge_2a && st->kh == 1 && !st->in2 && st->relu) a.merge_accumulators = 1;
-          auto bytes_of = [&](const Tensor* t) { return t ? static_cast<size_t>(a.n) * (t->elems() / t->n) * 4 : 0; };
-          if (hints) {
-            const bool evict_first_on = (hints & 1) != 0, weights_on = (hints & 2) != 0, out_last_on = (hints & 4) != 0;
-            int h = 0;
-            if (evict_first_on && bytes_of(st->in) > small) h |= 1;
-            if (out_last_on && bytes_of(st->out) <= small) h |= 2 << 2;
-            else if (evict_first_on && bytes_of(st->out) > small) h |= 1 << 2;
-            if (evict_first_on && st->in2 && bytes_of(st->in2) > small) h |= 1 << 4;
-            if (weights_on) h |= 2 << 6;
-            a.l2_hints = h;
-          }
-          ++conv_index;
-        }
+        a.weights_evict_last = weights_last ? 1 : 0;
         DC_CHECK(dc_conv_forward(&a, stream));
         break;
       }

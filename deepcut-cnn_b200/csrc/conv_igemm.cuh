@@ -89,12 +89,8 @@ struct ConvParams {
   int debug_skip;           // MICROBENCHMARK ONLY (wrong results): after the first pipeline fill the producer stops loading the weight
                             // tiles (bit 0) / the activation tiles (bit 1); the MMAs run on whatever the stages hold.  Gives the time a
                             // weight-resident / activation-resident variant of a layer could reach before building it (DC_DEBUG_SKIP)
-  int merge_acc;            // experiment: all three products into ONE accumulator (no separate cross terms): what BN = 256 tiles would
-                            // need to keep double-buffered accumulators in 512 TMEM columns; costs RZ-accumulation bias
-  int reverse;              // walk the work units from the last to the first: a layer that starts where its producer just finished
-                            // finds the most recently written part of its input still in L2 (serpentine schedule, dc_engine.cpp)
-  int l2_hints;             // L2 eviction priorities, 2 bits each (0 normal, 1 evict_first, 2 evict_last): [1:0] activations in,
-                            // [3:2] output, [5:4] residual, [7:6] weights
+  int w_evict_last;         // weight tiles are loaded with the L2 evict_last priority (every CTA re-reads them for each of its pixel tiles
+                            // while the activations stream through L2: -2 % of the 16x720p step, profiles/r2_chunk_sweep.md)
   float* sk_ws;             // split-K scratch: [unit][peer - 1][BN columns][128 rows] fp32 partial tiles (global memory, L2-resident)
 };
 
@@ -212,14 +208,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint64_t pol_a = l2_policy(p.l2_hints & 3), pol_w = l2_policy((p.l2_hints >> 6) & 3);
+      const uint64_t pol_w = l2_policy(p.w_evict_last ? 2 : 0);
       // Weights do not depend on the predecessor kernel: the weight tiles of this CTA's first K-steps (one per pipeline
       // stage) are requested BEFORE griddepcontrol.wait, so their HBM latency (a single image re-reads all 251 MB of
       // packed weights from HBM every forward) overlaps the predecessor's tail; the activation tiles follow after the wait.
       int npre = 0;
       if (p.early_weights && unit_first < total_units) {
         int q0, nt0;
-        fastdivmod(p.div_ntn, p.reverse ? total_units - 1 - unit_first : unit_first, q0, nt0);
+        fastdivmod(p.div_ntn, unit_first, q0, nt0);
         const int n0 = nt0 * BN + cta_rank * Cfg::kBRows;
         for (int ks = ks_begin; ks < ks_end && npre < kStages; ++ks, ++npre) {
           uint8_t* sa = smem + npre * Cfg::kStageBytes;
@@ -238,8 +234,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;
-      for (int it = unit_first; it < total_units; it += unit_stride) {
-        const int unit = p.reverse ? total_units - 1 - it : it;
+      for (int unit = unit_first; unit < total_units; unit += unit_stride) {
         int nt, mt, tx, ty, img;
         decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BN + cta_rank * Cfg::kBRows;
@@ -251,7 +246,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             const int kcoord = (t * kchunks + kc) * kBK;
             const bool fresh = issued >= npre;      // else: this stage's barrier is armed and its weight tiles are on their way
-            if (p.debug_skip && issued >= kStages) {
+            if (SK == 0 && p.debug_skip && issued >= kStages) {
               // microbenchmark mode: arm the barrier for exactly what is still loaded
               const bool ld_a = !(p.debug_skip & 2), ld_b = !(p.debug_skip & 1);
               const uint32_t bytes = (ld_a ? 2u * Cfg::kABytes : 0u) + (ld_b ? 2u * Cfg::kBBytes : 0u);
@@ -259,8 +254,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (CG == 2) {
                 if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);
                 if (ld_a) {
-                  tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
-                  tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
+                  tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
+                  tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
                 }
                 if (ld_b) {
                   tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
@@ -269,8 +264,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               } else {
                 mbar_expect_tx(&full_bar[stage], bytes);
                 if (ld_a) {
-                  tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
-                  tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
+                  tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
+                  tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
                 }
                 if (ld_b) {
                   tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
@@ -284,16 +279,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (CG == 2) {
               // both CTAs' loads count on the leader's barrier; only the leader arms it (for both halves)
               if (cta_rank == 0 && fresh) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
-              tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
+              tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
+              tma_load_5d_2cta(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
               if (fresh) {
                 tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
                 tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
               }
             } else {
               if (fresh) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0, pol_a);
-              tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1, pol_a);
+              tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
+              tma_load_5d(sa + Cfg::kABytes, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 1);
               if (fresh) {
                 tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[stage], kcoord, n0, 0, pol_w);
                 tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
@@ -317,7 +312,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 2 * BN);   // main
-        const uint32_t dx = p.merge_acc ? d : d + BN;                          // cross terms
+        const uint32_t dx = d + BN;                                            // cross terms
         uint32_t accum = 0;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
           mbar_wait(&full_bar[stage], phase);
@@ -333,7 +328,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // hi*hi, hi*lo and lo*hi are symmetric in (A, B): swapping the operands only transposes D
             if (CG == 2) {
               umma_f16_2cta(d, a_hi + adv, b_hi + adv, idesc, accum);
-              umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, p.merge_acc ? 1u : accum);
+              umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, accum);
               accum = 1;
               umma_f16_2cta(dx, a_lo + adv, b_hi + adv, idesc, 1);
             } else if (p.swap_ab) {
@@ -372,10 +367,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int piece = lane & 3;
     const int own_sw = (lane >> 1) & 3;
     const bool has_res = p.res != nullptr;
-    const uint64_t pol_o = l2_policy((p.l2_hints >> 2) & 3), pol_r = l2_policy((p.l2_hints >> 4) & 3);
-    auto issue_residual = [&](int it_) {
-      if (it_ >= total_units) return;
-      const int u = p.reverse ? total_units - 1 - it_ : it_;
+    auto issue_residual = [&](int u) {
+      if (u >= total_units) return;
       int t_nt, t_mt, t_tx, t_ty, t_img;
       decode_unit<CG>(p, u, cta_rank, t_nt, t_mt, t_tx, t_ty, t_img);
       if (t_mt >= p.n_tiles_m || t_nt * BN + c0 >= p.Cout) return;
@@ -389,8 +382,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (yy0 + dy < p.Ho && xx0 + dx < p.Wo) {      // rows outside the image are clipped by the TMA store: leave garbage
           const __half* src = base + (pix0 + dy * p.Wo + dx) * p.Cout;
           uint8_t* dst = stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4);
-          cp_async_16(dst, src, pol_r);
-          cp_async_16(dst + 2048, src + p.res_plane, pol_r);
+          cp_async_16(dst, src);
+          cp_async_16(dst + 2048, src + p.res_plane);
         }
       }
       cp_async_commit();
@@ -398,8 +391,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (has_res) issue_residual(unit_first);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int it = unit_first; it < total_units; it += unit_stride) {
-      const int unit = p.reverse ? total_units - 1 - it : it;
+    for (int unit = unit_first; unit < total_units; unit += unit_stride) {
       int nt, mt, tx, ty, img;
       decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
       const int n0 = nt * BN;
@@ -474,8 +466,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
           const int r0 = q * 32;
           const int box_x = tx * p.TW + (r0 & (p.TW - 1)), box_y = ty * p.TH + (r0 >> p.log2_tw);
-          tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0, pol_o);
-          tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1, pol_o);
+          tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
+          tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
           tma_store_commit();
           tma_store_wait_read();                                  // staging tile drained: safe to refill
         }
@@ -488,7 +480,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      if (has_res) issue_residual(it + unit_stride);
+      if (has_res) issue_residual(unit + unit_stride);
       if (++acc == Cfg::kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();
@@ -498,14 +490,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;       // which of the two warps of this quarter
     const int row = q * 32 + lane;          // accumulator row (TMEM lane) this thread owns
-    const uint64_t pol_o = l2_policy((p.l2_hints >> 2) & 3);
     // residual prefetch registers (split-NHWC mode): 4 rows x {hi, lo} x 16 B of the NEXT chunk
     uint4 res_h[4], res_l[4];
-    auto prefetch_residual = [&](int it_, int c0) {
+    auto prefetch_residual = [&](int u, int c0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0); }
-      if (it_ >= total_units) return;
-      const int u = p.reverse ? total_units - 1 - it_ : it_;
+      if (u >= total_units) return;
       int t_nt, t_mt, t_tx, t_ty, t_img;
       decode_unit<CG>(p, u, cta_rank, t_nt, t_mt, t_tx, t_ty, t_img);
       if (t_mt >= p.n_tiles_m) return;
@@ -548,8 +538,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int it = unit_first; it < total_units; it += unit_stride) {
-      const int unit = (SK == 0 && p.reverse) ? total_units - 1 - it : it;     // split-K launches (one unit per cluster) never reverse
+    for (int unit = unit_first; unit < total_units; unit += unit_stride) {
       int nt, mt, tx, ty, img;
       decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
       const bool tile_ok = mt < p.n_tiles_m;       // the odd CTA of the last pair may own a phantom tile
@@ -629,7 +618,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (n0 + c0 >= p.Cout) {
             // ragged last channel tile: nothing to do here, but if this was the warp's first chunk the
             // prefetch registers still hold the zeros meant for it -- refill them for the next tile
-            if (p.res != nullptr && c0 == half * 32) prefetch_residual(it + unit_stride, half * 32);
+            if (p.res != nullptr && c0 == half * 32) prefetch_residual(unit + unit_stride, half * 32);
             break;
           }
           uint32_t r[32], rx[32];
@@ -647,8 +636,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             __syncwarp();
             // prefetch the residual of the chunk this warp handles next (same tile, or the next tile's first)
-            int nunit = it, nc0 = c0 + 64;
-            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { nunit = it + unit_stride; nc0 = half * 32; }
+            int nunit = unit, nc0 = c0 + 64;
+            if (nc0 >= BN || nt * BN + nc0 >= p.Cout) { nunit = unit + unit_stride; nc0 = half * 32; }
             prefetch_residual(nunit, nc0);
           }
           float sc[32], sh[32];
@@ -660,10 +649,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             sh[4 * g] = b4.x; sh[4 * g + 1] = b4.y; sh[4 * g + 2] = b4.z; sh[4 * g + 3] = b4.w;
           }
           tmem_ld_wait();
-          if (p.merge_acc) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) rx[j] = 0u;
-          }
           if constexpr (SK != 0) add_partials(r, rx, c0);
           float v[32];
 #pragma unroll
@@ -704,8 +689,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0) {
-            tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0, pol_o);
-            tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1, pol_o);
+            tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
+            tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
             tma_store_commit();
           }
         }

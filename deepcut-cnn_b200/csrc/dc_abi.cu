@@ -621,12 +621,9 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.swap_ab = a->out_f32_rows == 2;
   p.early_weights = use_early_weights();
   { const char* e = getenv("DC_DEBUG_SKIP"); p.debug_skip = e ? (atoi(e) & 3) : 0; }      // microbenchmarks only: results are wrong
-  p.reverse = a->reverse_units ? 1 : 0;
-  p.l2_hints = a->l2_hints & 0xFF;
   // weights evict_last pays when every CTA re-reads the layer's weight tiles for many pixel tiles; a launch with fewer pixel tiles than
   // SMs (a single image) reads each weight tile once, and 251 MB of evict_last lines per forward would only push the activations out
-  static const bool hint_small = [] { const char* e = getenv("DC_L2_HINTS_SMALL"); return e && e[0] == '1'; }();     // A/B switch
-  if (!hint_small && ((p.l2_hints >> 6) & 3) == 2 && p.n_tiles_m < g_num_sms) p.l2_hints &= ~0xC0;
+  p.w_evict_last = (a->weights_evict_last && p.n_tiles_m >= g_num_sms) ? 1 : 0;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
 
   CUtensorMap ta, tb, to;
@@ -677,7 +674,6 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (ksplit > 1) return bn == 128 ? launch_conv<128, 1, 8, 1>(ta, tb, to, p, st, ksplit) : launch_conv<64, 1, 8, 1>(ta, tb, to, p, st, ksplit);
   // epilogue-bound layers (short K, wide output: the 1x1 expand convs) get the 16-warp lean epilogue
-  p.merge_acc = (a->merge_accumulators && pair && !(pair && lean_shape) && p.out_mode == dc::kOutSplitNHWC) ? 1 : 0;
   const bool lean = pair && lean_shape;
   if (lean) return launch_conv<128, 2, 16>(ta, tb, to, p, st);
   if (wide256) return launch_conv<256, 2, 8>(ta, tb, to, p, st);

@@ -67,6 +67,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// -DDC_PTX_NO_CACHE_HINT compiles every access below WITHOUT the .L2::cache_hint qualifier (the policy operand is ignored): the A/B
+// build that isolates what the hinted instruction forms themselves cost.
+#ifdef DC_PTX_NO_CACHE_HINT
+#define DC_HINT(q) ""
+#define DC_HINT_ARG(n) ""
+#else
+#define DC_HINT(q) q
+#define DC_HINT_ARG(n) ", %" #n
+#endif
+
 // L2 eviction-priority policy for bulk-tensor / cp.async accesses: 0 = normal, 1 = evict_first (streamed once: do not let it
 // push reusable lines out), 2 = evict_last (small tensor the next kernel re-reads: keep it in the 126 MB L2)
 __device__ __forceinline__ uint64_t l2_policy(int kind) {
@@ -78,17 +88,17 @@ __device__ __forceinline__ uint64_t l2_policy(int kind) {
 }
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4, uint64_t policy) {
+                                            int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes" DC_HINT(".L2::cache_hint")
+      " [%0], [%1, {%3, %4, %5}], [%2]" DC_HINT_ARG(6) ";" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
@@ -98,17 +108,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
 // the pair's even CTA within the shared::cluster window.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 __device__ __forceinline__ void tma_load_5d_2cta(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                                 int c3, int c4, uint64_t policy) {
+                                                 int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2cta(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes" DC_HINT(".L2::cache_hint")
+      " [%0], [%1, {%3, %4, %5}], [%2]" DC_HINT_ARG(6) ";" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
@@ -159,11 +169,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // smem -> global bulk tensor store (bulk async-group completion); OOB parts of the box are clipped
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4, uint64_t policy) {
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;" ::"l"(
+      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
           reinterpret_cast<uint64_t>(m)),
-      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -266,8 +276,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
 }
 
 // Ampere-style 16-byte async copy global -> shared (LDGSTS), bypassing registers
-__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "l"(policy) : "memory");
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

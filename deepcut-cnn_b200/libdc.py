@@ -14,7 +14,7 @@ class ConvArgs(C.Structure):
                 ("relu", C.c_int), ("out_f32_rows", C.c_int), ("ldc", C.c_int), ("out", C.c_void_p), ("stride", C.c_int),
                 ("splitk_workspace", C.c_void_p), ("splitk_workspace_bytes", C.c_size_t),
                 ("x_plane", C.c_longlong), ("out_plane", C.c_longlong), ("residual_plane", C.c_longlong),
-                ("reverse_units", C.c_int), ("l2_hints", C.c_int), ("merge_accumulators", C.c_int)]
+                ("weights_evict_last", C.c_int)]
 
 
 _SIGS = {

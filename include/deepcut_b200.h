@@ -127,12 +127,9 @@ typedef struct dc_conv_args {
    * larger [2][N][..] tensor, n being the images this launch covers; the distance between the hi and the lo plane is then
    * the FULL tensor's plane, given here in elements.  0 = dense (n*h*w*c of the tensor itself). */
   long long x_plane, out_plane, residual_plane;
-  /* Scheduling hints (0 = none).  reverse_units: walk the launch's tiles from the last to the first, so that a layer starting
-   * where its producer just finished finds the tail of its input still in L2.  l2_hints: L2 eviction priority, 2 bits per
-   * operand (0 normal, 1 evict_first, 2 evict_last): bits [1:0] x, [3:2] out, [5:4] residual, [7:6] weights. */
-  int reverse_units;
-  int l2_hints;
-  int merge_accumulators;    /* experiment (CTA-pair kernels with split output only): hi*hi, hi*lo and lo*hi into one TMEM accumulator */
+  /* 1: load the weight tiles with the L2 evict_last priority (they are re-read by every CTA for each of its pixel tiles while the
+   * activations stream through L2).  Ignored for launches with fewer pixel tiles than SMs, which read each weight tile once. */
+  int weights_evict_last;
 } dc_conv_args;
 /* Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-24) =
  * im2col_gpu (util/im2col.cu:8-62) + cublasSgemm (util/math_functions.cu:13-27) per image, and the
