@@ -77,6 +77,11 @@ class Net {
   void set_fusion(bool on);
   bool fusion() const { return fusion_; }
   void materialize_intermediates(bool on);
+  // Net outputs the caller will not read (e.g. "next_pred": estimate_pose.py:231 reads only prob and loc_pred).  The fused plan
+  // leaves every head whose final blob is named here out of its merged head GEMMs and writes nothing to that blob (it reads as
+  // "not written by the last forward", blob_fresh() == false).  Per-layer execution ignores the list and computes everything.
+  void set_skipped_outputs(const vector<string>& blob_names);
+  const set<string>& skipped_outputs() const { return skipped_outputs_; }
   bool fused_last_forward() const { return fused_last_forward_; }
   // Why the planner declined (empty when the fused plan is active).
   const string& fusion_diagnostic() const { return fusion_diag_; }
@@ -120,6 +125,7 @@ class Net {
 
   bool fusion_ = true;
   bool materialize_ = false;
+  set<string> skipped_outputs_;
   bool step_timing_ = false;
   bool fused_last_forward_ = false;
   string fusion_diag_;

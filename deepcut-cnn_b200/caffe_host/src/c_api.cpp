@@ -120,6 +120,17 @@ int caffe_blob_data_head(void* blob) {
 
 int caffe_net_set_fusion(void* net, int on) { return Guard([&] { N(net)->set_fusion(on != 0); }); }
 int caffe_net_materialize_intermediates(void* net, int on) { return Guard([&] { N(net)->materialize_intermediates(on != 0); }); }
+int caffe_net_set_skipped_outputs(void* net, const char* comma_separated_blob_names) {
+  return Guard([&] {
+    std::vector<std::string> names;
+    std::string cur;
+    for (const char* c = comma_separated_blob_names ? comma_separated_blob_names : ""; ; ++c) {
+      if (*c == ',' || *c == 0) { if (!cur.empty()) names.push_back(cur); cur.clear(); if (*c == 0) break; }
+      else if (*c != ' ') cur += *c;
+    }
+    N(net)->set_skipped_outputs(names);
+  });
+}
 int caffe_net_fused_last_forward(void* net) { return N(net)->fused_last_forward(); }
 const char* caffe_net_fusion_diagnostic(void* net) { return N(net)->fusion_diagnostic().c_str(); }
 long long caffe_net_last_forward_launches(void* net) { return N(net)->last_forward_launches(); }

@@ -331,6 +331,25 @@ struct Matcher {
       heads.push_back(hd);
     }
     if (heads.empty()) return Fail("no head matched");
+    // heads whose final blob the caller declared unread (Net::set_skipped_outputs) are matched -- their layers count as done,
+    // their values as fused away -- but take no rows of the merged GEMMs and get no finishing step
+    std::vector<Head> skipped;
+    std::string skip_tag;
+    if (!net.skipped_outputs().empty()) {
+      std::vector<Head> kept;
+      for (const Head& h : heads) {
+        const FusedPlan::Tensor* o = tensors[top_t[h.sig >= 0 ? h.sig : h.elt][0]];
+        const bool skip = o->blob >= 0 && net.skipped_outputs().count(net.blob_names()[o->blob]) != 0;
+        (skip ? skipped : kept).push_back(h);
+        if (skip) skip_tag += "-" + net.blob_names()[o->blob];
+      }
+      if (kept.empty()) return Fail("every head output is in the skipped set");
+      heads.swap(kept);
+    }
+    for (const Head& h : skipped) {
+      for (int l : {h.deconv, h.skipconv, h.crop, h.elt}) { tensors[top_t[l][0]]->kind = FusedPlan::Tensor::kVirtual; done[l] = 1; }
+      if (h.sig >= 0) { tensors[top_t[h.sig][0]]->kind = FusedPlan::Tensor::kVirtual; done[h.sig] = 1; }
+    }
     int ctot = 0;
     for (const Head& h : heads) ctot += As<ConvBase>(net.layers()[h.deconv].get())->num_output();
     // what the merged channel-major GEMMs (dc_conv_forward, out_f32_rows = 2) need: 128-row weight tiles, i.e. more than 64
@@ -349,11 +368,12 @@ struct Matcher {
     auto round32 = [](long long v) { return static_cast<int>((v + 31) / 32 * 32); };
     FusedPlan::Tensor* col = NewInternal(FusedPlan::Tensor::kF32Rows, 1, 1, dc_packed_rows(ctot * 9), 1);
     col->ld = round32(static_cast<long long>(x5->n) * h5 * w5);
-    FusedPlan::Step* g1 = AddStep(FusedPlan::Step::kHeadGemm, "heads/deconv_gemm");
+    // (the names carry the skipped set: the packed-weight cache is keyed by step type + name)
+    FusedPlan::Step* g1 = AddStep(FusedPlan::Step::kHeadGemm, "heads/deconv_gemm" + skip_tag);
     g1->in = x5; g1->out = col; g1->deconv_rows = true; g1->cout = ctot * 9;
     FusedPlan::Tensor* srows = NewInternal(FusedPlan::Tensor::kF32Rows, 1, 1, dc_packed_rows(skip_rows), 1);
     srows->ld = round32(static_cast<long long>(x3->n) * h3 * w3);
-    FusedPlan::Step* g2 = AddStep(FusedPlan::Step::kHeadGemm, "heads/skip_gemm");
+    FusedPlan::Step* g2 = AddStep(FusedPlan::Step::kHeadGemm, "heads/skip_gemm" + skip_tag);
     g2->in = x3; g2->out = srows; g2->deconv_rows = false; g2->cout = skip_rows;
     int off = 0;
     for (const Head& h : heads) {

@@ -252,6 +252,15 @@ void Net<Dtype>::Reshape() {
 
 template <typename Dtype> void Net<Dtype>::set_fusion(bool on) { fusion_ = on; }
 template <typename Dtype> void Net<Dtype>::materialize_intermediates(bool on) { if (on != materialize_) { materialize_ = on; delete plan_; plan_ = nullptr; } }
+template <typename Dtype> void Net<Dtype>::set_skipped_outputs(const vector<string>& blob_names) {
+  set<string> want(blob_names.begin(), blob_names.end());
+  for (const string& n : want) {
+    bool is_output = false;
+    for (int b : net_output_blob_indices_) is_output = is_output || blob_names_[b] == n;
+    CHECK(is_output) << "set_skipped_outputs: '" << n << "' is not an output blob of this net";
+  }
+  if (want != skipped_outputs_) { skipped_outputs_.swap(want); delete plan_; plan_ = nullptr; }
+}
 template <typename Dtype> void Net<Dtype>::InvalidatePlan() { delete plan_; plan_ = nullptr; plan_weights_.reset(); }
 
 // --------------------------------------------------------------------------------------- weights

@@ -31,6 +31,14 @@
 
 namespace dc {
 
+// The lane of the producer / MMA warp that issues TMA loads and MMAs: elected with elect.sync inside converged code (see the producer).
+// -DDC_ISSUE_LANE0 builds the round-1 form (`lane == 0`, every issue wrapped in ptxas's per-lane waterfall) for A/B runs.
+#ifdef DC_ISSUE_LANE0
+#define DC_ISSUER_LANE() (lane == 0)
+#else
+#define DC_ISSUER_LANE() elect_one()
+#endif
+
 constexpr int kBM = 128;        // output pixels per tile (TMEM lanes)
 constexpr int kBK = 64;         // fp16 channels per K-chunk = one 128-byte swizzle row
 constexpr int kMaxTaps = 9;
@@ -207,7 +215,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop converged and ONE ELECTED lane issues (elect.sync).  Under `if (lane == 0)` ptxas cannot prove
+    // that the operands of the uniform-datapath instructions (UTMALDG here, UTCHMMA / UTCBAR in the MMA warp) are warp-uniform and
+    // wraps every one of them in a per-lane waterfall (ELECT, four or five R2UR.BROADCAST, two PLOP3, a back branch: ~14 SASS
+    // instructions per instruction issued); inside an elect.sync region of converged code they are plain uniform-register operands.
+    {
       const uint64_t pol_w = l2_policy(p.w_evict_last ? 2 : 0);
       // Weights do not depend on the predecessor kernel: the weight tiles of this CTA's first K-steps (one per pipeline
       // stage) are requested BEFORE griddepcontrol.wait, so their HBM latency (a single image re-reads all 251 MB of
@@ -219,15 +231,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int n0 = nt0 * BN + cta_rank * Cfg::kBRows;
         for (int ks = ks_begin; ks < ks_end && npre < kStages; ++ks, ++npre) {
           uint8_t* sa = smem + npre * Cfg::kStageBytes;
-          if (CG == 2) {
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[npre], 2 * Cfg::kStageBytes);
-            tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
-            tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
-          } else {
-            mbar_expect_tx(&full_bar[npre], Cfg::kStageBytes);
-            tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
-            tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
+          if (DC_ISSUER_LANE()) {
+            if (CG == 2) {
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[npre], 2 * Cfg::kStageBytes);
+              tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
+              tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
+            } else {
+              mbar_expect_tx(&full_bar[npre], Cfg::kStageBytes);
+              tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
+              tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
+            }
           }
+          __syncwarp();
         }
       }
       pdl_wait();
@@ -251,7 +266,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const bool ld_a = !(p.debug_skip & 2), ld_b = !(p.debug_skip & 1);
               const uint32_t bytes = (ld_a ? 2u * Cfg::kABytes : 0u) + (ld_b ? 2u * Cfg::kBBytes : 0u);
               ++issued;
-              if (CG == 2) {
+              if (!DC_ISSUER_LANE()) {
+              } else if (CG == 2) {
                 if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);
                 if (ld_a) {
                   tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
@@ -272,11 +288,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
                 }
               }
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1; }
               continue;
             }
             ++issued;
-            if (CG == 2) {
+            if (!DC_ISSUER_LANE()) {
+            } else if (CG == 2) {
               // both CTAs' loads count on the leader's barrier; only the leader arms it (for both halves)
               if (cta_rank == 0 && fresh) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
               tma_load_5d_2cta(sa, &tmA, &full_bar[stage], kc * kBK, ix, iy, img, 0);
@@ -294,6 +312,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[stage], kcoord, n0, 1, pol_w);
               }
             }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -301,7 +320,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {             // the leader CTA issues for the whole group
+    if (cta_rank == 0) {             // the leader CTA issues for the whole group: converged warp, one elected lane per K-step (see the producer)
       constexpr uint32_t idesc = umma_idesc_f16(kBM * CG, BN);
       [[maybe_unused]] constexpr uint32_t idesc_wide = umma_idesc_f16(kBM, 2 * BN);     // CG = 1: fused hi*hi | hi*lo
       int stage = 0;
@@ -313,7 +332,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 2 * BN);   // main
         const uint32_t dx = d + BN;                                            // cross terms
-        uint32_t accum = 0;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -322,33 +340,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t a_lo = umma_desc_k_sw128(sa + Cfg::kABytes);
           const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * Cfg::kABytes);
           const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
+          const uint32_t later = ks != ks_begin;      // 0 on the unit's first K-step: its first MMAs overwrite the accumulators
+          if (DC_ISSUER_LANE()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);   // 16 fp16 = 32 B along K
-            // hi*hi, hi*lo and lo*hi are symmetric in (A, B): swapping the operands only transposes D
-            if (CG == 2) {
-              umma_f16_2cta(d, a_hi + adv, b_hi + adv, idesc, accum);
-              umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, accum);
-              accum = 1;
-              umma_f16_2cta(dx, a_lo + adv, b_hi + adv, idesc, 1);
-            } else if (p.swap_ab) {
-              // hi*hi and hi*lo share their M-side operand: one MMA with N = 2*BN over the stacked [a_hi; a_lo] rows
-              // (contiguous in the stage) writes main | cross side by side and reads the shared operand once
-              umma_f16(d, b_hi + adv, a_hi + adv, idesc_wide, accum);
-              accum = 1;
-              umma_f16(dx, b_lo + adv, a_hi + adv, idesc, 1);
-            } else {
-              umma_f16(d, a_hi + adv, b_hi + adv, idesc_wide, accum);      // [b_hi; b_lo] rows are contiguous too
-              accum = 1;
-              umma_f16(dx, a_lo + adv, b_hi + adv, idesc, 1);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);   // 16 fp16 = 32 B along K
+              const uint32_t accum = k > 0 ? 1u : later;
+              // hi*hi, hi*lo and lo*hi are symmetric in (A, B): swapping the operands only transposes D
+              if (CG == 2) {
+                umma_f16_2cta(d, a_hi + adv, b_hi + adv, idesc, accum);
+                umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, accum);
+                umma_f16_2cta(dx, a_lo + adv, b_hi + adv, idesc, 1);
+              } else if (p.swap_ab) {
+                // hi*hi and hi*lo share their M-side operand: one MMA with N = 2*BN over the stacked [a_hi; a_lo] rows
+                // (contiguous in the stage) writes main | cross side by side and reads the shared operand once
+                umma_f16(d, b_hi + adv, a_hi + adv, idesc_wide, accum);
+                umma_f16(dx, b_lo + adv, a_hi + adv, idesc, 1);
+              } else {
+                umma_f16(d, a_hi + adv, b_hi + adv, idesc_wide, accum);      // [b_hi; b_lo] rows are contiguous too
+                umma_f16(dx, a_lo + adv, b_hi + adv, idesc, 1);
+              }
+            }
+            if (CG == 2) umma_commit_2cta(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
+            if (ks + 1 == ks_end) {                 // the unit's last K-step: publish the accumulators
+              if (CG == 2) umma_commit_2cta(&tfull_bar[acc]);
+              else umma_commit(&tfull_bar[acc]);
             }
           }
-          if (CG == 2) umma_commit_2cta(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) umma_commit_2cta(&tfull_bar[acc]);
-        else umma_commit(&tfull_bar[acc]);
         if (++acc == Cfg::kAccBufs) { acc = 0; acc_phase ^= 1; }
       }
     }

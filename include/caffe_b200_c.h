@@ -64,6 +64,9 @@ int caffe_blob_data_head(void* blob);
 /* B200 extensions */
 int caffe_net_set_fusion(void* net, int on);
 int caffe_net_materialize_intermediates(void* net, int on);
+/* Net outputs the caller will not read ("next_pred": python/pose/estimate_pose.py:231 reads prob and loc_pred only): the fused
+ * plan drops their heads from the merged head GEMMs and leaves those blobs unwritten (caffe_net_blob_fresh() == 0).  "" clears. */
+int caffe_net_set_skipped_outputs(void* net, const char* comma_separated_blob_names);
 int caffe_net_fused_last_forward(void* net);
 const char* caffe_net_fusion_diagnostic(void* net);
 long long caffe_net_last_forward_launches(void* net);

@@ -20,6 +20,28 @@ def test_generated_prototxt_equals_reference_structure():
     assert ref == gen           # name, input, input_dim and all 680 layers, field for field
 
 
+def test_product_loader_reads_the_reference_prototxt_itself():
+    # the C++ prototxt loader + Net::Init on the file the reference ships (models/deepercut/ResNet-152.prototxt, incl. its
+    # `stride: 1 #2` trailing comments), not on this repo's generated twin: same layers, blobs and parameter shapes as the oracle's
+    # independent parser + graph builder derive from that file
+    if not os.path.exists(REF_PROTOTXT):
+        pytest.skip("reference not mounted on this box")
+    net = caffe.Net(REF_PROTOTXT, caffe.TEST)
+    onet = caffe_ref.load_net(REF_PROTOTXT)
+    assert [n for n in net._layer_names if "_split" not in n] == [opt.get(l, "name") for l in onet.layers]
+    assert len(onet.layers) == 680
+    assert net.inputs == ["data"] and net.outputs == ["loc_pred", "next_pred", "prob"]
+    for name, shape in onet.blob_shapes.items():
+        assert tuple(net.blobs[name].shape) == tuple(shape), name
+    for lname, shapes in onet.param_shapes.items():
+        assert [tuple(b.shape) for b in net.params[lname]] == [tuple(s) for s in shapes], lname
+    # the dilated stages as the file states them (res5a_branch2b: 3x3, pad 2, dilation 2 on a stride-1 res5)
+    ref = opt.parse_file(REF_PROTOTXT)
+    conv = {opt.get(l, "name"): l for l in ref["layer"]}["res5a_branch2b"]["convolution_param"][0]
+    assert (conv.get("dilation"), conv.get("pad"), conv.get("stride", [1])) == ([2], [2], [1])
+    assert tuple(net.blobs["res5c"].shape[1:2]) == (2048,)
+
+
 def test_both_parsers_agree():
     txt = dcutil.gen_prototxt.generate(height=64, width=96)
     a, b = opt.parse(txt), dcutil.ptx.parse(txt)

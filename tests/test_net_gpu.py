@@ -240,6 +240,37 @@ def test_full_depth_nets_match_oracle(tmp_path, stages, h, w, n):
     assert 0.01 < got["prob"].min() and got["prob"].max() < 0.99
 
 
+def test_survey_recipe_uncalibrated_weights_relative_tolerance(tmp_path):
+    """SURVEY 8(d)'s own weight recipe (`synth.weights`: MSRA convs, BatchNorm statistics NOT matched to the activations), which
+    every other whole-net test replaces by calibrated statistics.  With it the activations grow geometrically through the 50
+    residual adds (|res5c| ~ 1e3..1e4, logits ~ 1e3, `prob` pinned at 0 / 1), so the absolute 1e-3 budget is not meaningful; the
+    product must still track the reference's CPU layers to fp32 relative accuracy: max|got - ref| <= 2e-5 * max|ref| on the two
+    regression outputs (fp64 emulation of the split-fp16 operands, tests/torch_model.py: 2.3e-6; the reference's own fp32-vs-fp64
+    distance: 7e-7).  `prob` is the sigmoid of logits of magnitude ~1e3: the same relative error is ~5e-3 absolute on a logit,
+    i.e. up to ~1e-3 on the 0.6 % of `prob` values that are not saturated (emulation: 1.1e-3) -- held to 5e-3 here."""
+    from oracle import caffe_ref
+    h, w = 128, 160
+    path = dcutil.write_prototxt(tmp_path, stages=(3, 8, 36, 3), height=h, width=w)
+    weights = dcutil.synth.weights(caffe_ref.load_net(path).typed_param_shapes())
+    x = dcutil.synth.images(1, h, w, seed=88)
+    if netutil.reference_available():
+        ref = netutil.reference_forward(path, weights, x, want=["prob", "loc_pred", "next_pred"])
+    else:
+        ref = netutil.oracle_forward(path, weights, x)
+    net = netutil.product_net(path, weights)
+    got = netutil.product_forward(net, x)
+    assert net.fused_last_forward, net.fusion_diagnostic
+    rel = {}
+    for k in ("loc_pred", "next_pred"):
+        scale = float(np.abs(ref[k]).max())
+        assert scale > 10.0, (k, scale)          # the recipe really is the uncalibrated one
+        rel[k] = netutil.max_err(got[k], ref[k]) / scale
+    print("\n[parity] survey recipe (uncalibrated) ResNet-152 %dx%d: relative %s, |loc_pred| max %.3g" %
+          (h, w, rel, float(np.abs(ref["loc_pred"]).max())))
+    assert max(rel.values()) < 2e-5, rel
+    assert netutil.max_err(got["prob"], ref["prob"]) < 5e-3
+
+
 @pytest.mark.parametrize("n,h,w", [(1, 107, 93), (3, 65, 130), (2, 33, 47), (1, 200, 17), (1, 16, 16), (2, 8, 8), (1, 9, 40), (40, 32, 32)])
 def test_ragged_input_sizes(tmp_path, n, h, w):
     """Sizes that are no multiple of the net's strides: every stage has an odd, ragged map (107x93 -> conv1 54x47 -> ceil-mode

@@ -113,6 +113,17 @@ if __name__ == "__main__":
         run(16, 45, 80, 512, 512, 3, 2, 2, 0, 0)
         run(16, 90, 160, 128, 512, 1, 0, 1, 1, 0)
         run(16, 180, 320, 64, 256, 1, 0, 1, 1, 0)
+    elif args.set == "pairs":      # the CTA-pair (cta_group::2) launches of res3 / res4 / res5: 1x1 reduce, 1x1 expand + shortcut
+        run(16, 90, 160, 512, 128, 1, 0, 1, 0, 0)
+        run(16, 90, 160, 128, 512, 1, 0, 1, 1, 0)
+        run(16, 45, 80, 1024, 256, 1, 0, 1, 0, 0)
+        run(16, 45, 80, 256, 1024, 1, 0, 1, 1, 0)
+        run(16, 45, 80, 256, 1024, 1, 0, 1, 0, 0)
+        run(16, 45, 80, 2048, 512, 1, 0, 1, 0, 0)
+        run(16, 45, 80, 512, 2048, 1, 0, 1, 1, 0)
+        run(16, 45, 80, 512, 2048, 1, 0, 1, 0, 0)
+        run(16, 45, 80, 256, 256, 3, 1, 1, 0, 0)
+        run(16, 45, 80, 512, 512, 3, 2, 2, 0, 0)
     elif args.set == "res2":
         run(16, 180, 320, 64, 64, 3, 1, 1, 0, 0)
         run(16, 180, 320, 64, 64, 1, 0, 1, 0, 0)
