@@ -525,6 +525,19 @@ def main():
                    "gpu_launches_per_image": int((L.dc_launch_count() - l0) // 50), "split_k_max": int(L.dc_get_split_k())}
         del lnet
 
+    # ---- the same workload for a caller that never reads next_pred (the demo, estimate_pose.py:231): net.skip_outputs drops the
+    # 364-channel head from the merged head GEMMs.  Reported beside the full-Net number, never instead of it.
+    subset = None
+    if rank == 0 and world == 1 and not args.no_latency_config and not args.only_exchange:
+        net.skip_outputs(["next_pred"])
+        for _ in range(3):
+            net.forward()
+        ksub = max(3, min(args.steps, 10))
+        sub_ms, _ = timed(net.forward, ksub)
+        subset = {"outputs": "prob, loc_pred (next_pred head skipped: net.skip_outputs)", "ms_per_step": sub_ms / ksub,
+                  "value": B * ksub / (sub_ms / 1e3), "unit": "images/s", "steps": ksub, "warmup": 3}
+        net.skip_outputs([])
+
     # ---- CPU baseline (oracle/_ref = the reference's CPU layers; numpy port if absent), rank 0 at N = 1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.only_exchange:
@@ -540,7 +553,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred", "mode": e2e_mode},
-                "exchange": exchange_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency,
+                "exchange": exchange_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency, "without_next_pred": subset,
                 "wall_ms_per_step": wall_ms / args.steps, "arena_mib": net.arena_bytes >> 20, "weights_mib": net.weight_bytes >> 20}
         emit(line)
     if dist is not None:

@@ -50,6 +50,7 @@ def _load():
                                      C.POINTER(C.c_double), ci]),
         "caffe_net_arena_bytes": (C.c_longlong, [vp]), "caffe_net_weight_bytes": (C.c_longlong, [vp]),
         "caffe_net_describe_plan": (ci, [vp, C.c_char_p, ci]), "caffe_net_blob_fresh": (ci, [vp, ci]),
+        "caffe_net_set_skipped_outputs": (ci, [vp, cs]),
         "caffe_net_set_debug_info": (ci, [vp, ci]), "caffe_net_debug_info": (ci, [vp, C.c_char_p, ci, C.POINTER(C.c_double), ci]),
     }
     for name, (res, args) in sig.items():

@@ -281,6 +281,8 @@ class Net(object):
                 end_ind = self._layer_names.index(end)
                 outputs = set([end] + blobs)
             self._forward(start_ind, end_ind)
+        if self.fused_last_forward:
+            outputs -= getattr(self, "_skipped", set())          # not computed (skip_outputs); per-layer forwards fill everything
         return _Outputs(self, sorted(outputs))
 
     def reshape(self):
@@ -295,6 +297,14 @@ class Net(object):
         check(lib.caffe_net_save(self._h, filename.encode()))
 
     # ---- B200 extensions
+    def skip_outputs(self, names):
+        """Declare net outputs this caller never reads (the demo reads `prob` and `loc_pred` only, estimate_pose.py:231): the
+        fused plan leaves their heads out of the merged head GEMMs (next_pred is 364 of the 406 head channels) and does not write
+        those blobs; forward() stops returning them and reading one raises.  `[]` restores the full net."""
+        names = [names] if isinstance(names, str) else list(names)
+        check(lib.caffe_net_set_skipped_outputs(self._h, ",".join(names).encode()))
+        self._skipped = set(names)
+
     def set_fusion(self, on):
         check(lib.caffe_net_set_fusion(self._h, int(bool(on))))
 

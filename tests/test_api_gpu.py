@@ -68,6 +68,31 @@ def test_net_trimmed_to_part_and_locref_heads_stays_fused(tmp_path):
         assert netutil.max_err(got[k], ref[k]) < 1e-4, k
 
 
+def test_skipped_outputs_leave_the_other_heads_bitwise_unchanged(tmp_path):
+    """net.skip_outputs(['next_pred']): the full deploy net, but the 364-channel head is neither computed nor written; prob and
+    loc_pred keep their per-element K chains (same weight rows, other row tiles), so they are bitwise what the full plan gives.
+    Reading the skipped blob raises instead of handing out stale data; clearing the list restores the full plan."""
+    path, weights = netutil.build(tmp_path, (1, 2, 2, 1), 96, 80)
+    x = dcutil.synth.images(3, 96, 80, seed=5)
+    net = netutil.product_net(path, weights)
+    full = netutil.product_forward(net, x)
+    launches_full = net.last_forward_launches
+    net.skip_outputs(["next_pred"])
+    got = netutil.product_forward(net, x)
+    assert net.fused_last_forward, net.fusion_diagnostic
+    assert sorted(got) == ["loc_pred", "prob"]
+    assert net.last_forward_launches == launches_full - 1            # one HeadFinish less; the two GEMMs shrink
+    for k in got:
+        assert np.array_equal(got[k], full[k]), (k, netutil.max_err(got[k], full[k]))
+    with pytest.raises(dcutil.caffe_module()._caffe.CaffeError, match="not written by the last forward"):
+        net.blobs["next_pred"].data
+    net.skip_outputs([])
+    again = netutil.product_forward(net, x)
+    assert sorted(again) == ["loc_pred", "next_pred", "prob"]
+    for k in again:
+        assert np.array_equal(again[k], full[k]), k
+
+
 def test_debug_info_probes_match_the_oracle_blob_by_blob(tmp_path):
     """debug_info (net.cpp:648-735): mean|x| of every top after every layer, here compared with the same statistic of the CPU
     oracle's blobs -- a per-blob check of the whole per-layer plugin path."""

@@ -76,3 +76,22 @@ def test_materialised_plans_do_not_chunk(tmp_path, monkeypatch):
     net.materialize_intermediates(True)
     desc = net.describe_plan()
     assert "launch groups" in desc
+
+
+def test_skipped_outputs_drop_their_heads_from_the_plan(tmp_path):
+    """Net::set_skipped_outputs (pycaffe shim: net.skip_outputs): a caller that never reads next_pred (estimate_pose.py:231 reads
+    prob and loc_pred) gets merged head GEMMs of 42 instead of 406 output channels and no finishing step for the skipped blob."""
+    caffe, net = _net(tmp_path, (1, 1, 1, 1), 2, 64, 64)
+    full = net.describe_plan()
+    assert len(re.findall(r"HeadFinish", full)) == 3 and "heads/deconv_gemm" in full
+    net.skip_outputs(["next_pred"])
+    trimmed = net.describe_plan()
+    assert len(re.findall(r"HeadFinish", trimmed)) == 2
+    assert "heads/deconv_gemm-next_pred" in trimmed and "next_pred/" not in trimmed.replace("gemm-next_pred", "")
+    net.skip_outputs([])
+    assert net.describe_plan() == full
+    with pytest.raises(caffe._caffe.CaffeError, match="not an output blob"):
+        net.skip_outputs(["res5c"])
+    with pytest.raises(caffe._caffe.CaffeError, match="every head output"):
+        net.skip_outputs(["prob", "loc_pred", "next_pred"])
+        net.describe_plan()
