@@ -800,22 +800,8 @@ void FusedPlan::UploadWeights(Net<float>& net) {
   PlanWeightCache& wc = *weights_;
   // steps are keyed by type + name: the same layers fuse the same way whatever the input shape
   auto key_of = [](const Step* st) { return std::to_string(static_cast<int>(st->type)) + (st->stem_tc ? "t:" : ":") + st->name; };
-  if (reuse) {
-    bool all = true;
-    for (Step* st : steps_)
-      if ((st->type == Step::kConv1 || st->type == Step::kConvBN || st->type == Step::kHeadGemm) && !wc.entries.count(key_of(st))) all = false;
-    if (all) {
-      for (Step* st : steps_) {
-        auto it = wc.entries.find(key_of(st));
-        if (it == wc.entries.end()) continue;
-        st->w_dev = it->second.w; st->scale_dev = it->second.scale; st->shift_dev = it->second.shift;
-      }
-      return;
-    }
-    weights_.reset(new PlanWeightCache());      // topology changed under the same weights: start over
-    weights_->Snapshot(net);
-    return UploadWeights(net);
-  }
+  // A cache that survived (same weights, new input shape or new option such as the skipped-outputs set) serves every step it has an
+  // entry for; steps it has never seen (another head grouping) are packed below and added to it.
   auto upload = [&](const void* host, size_t bytes) {
     void* d = nullptr;
     DC_CHECK(dc_malloc(&d, bytes));
@@ -845,6 +831,13 @@ void FusedPlan::UploadWeights(Net<float>& net) {
     }
   };
   for (Step* st : steps_) {
+    if (reuse) {
+      auto it = wc.entries.find(key_of(st));
+      if (it != wc.entries.end()) {
+        st->w_dev = it->second.w; st->scale_dev = it->second.scale; st->shift_dev = it->second.shift;
+        continue;
+      }
+    }
     if (st->type == Step::kConv1) {
       Layer<float>* cl = net.layers()[st->conv_layer].get();
       std::vector<float> a, b;

@@ -46,6 +46,7 @@ int g_num_sms = 0;
 // SMs the persistent conv grids leave free (dc_set_reserved_sms): a persistent kernel with one CTA per SM and a static tile schedule
 // cannot share its SMs -- a concurrent NCCL kernel that takes even a few of them delays the CTAs that should have run there by a whole
 // kernel, i.e. doubles that kernel's time.  While a batch exchange is in flight the forwards therefore run on SMs - reserve.
+constexpr int kDefaultL2Prefetch = 0;
 std::atomic<int> g_reserved_sms{[] { const char* e = getenv("DC_RESERVED_SMS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }()};
 int persistent_sms() {
   const int n = g_num_sms - g_reserved_sms.load();
@@ -625,6 +626,11 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   // SMs (a single image) reads each weight tile once, and 251 MB of evict_last lines per forward would only push the activations out
   p.w_evict_last = (a->weights_evict_last && p.n_tiles_m >= g_num_sms) ? 1 : 0;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
+  // HBM -> L2 prefetch distance (K-steps) for launches that stream their activations from HBM once: the stride-1 1x1 convs of a
+  // throughput-size batch (the 3x3 convs re-read theirs from L2, 94 % hit rate; a single image is latency-bound elsewhere).
+  // DC_L2_PREFETCH=<K-steps> overrides, 0 disables.
+  const int pf_dist = [] { const char* e = getenv("DC_L2_PREFETCH"); const int v = e ? atoi(e) : kDefaultL2Prefetch; return v < 0 ? 0 : (v > 64 ? 64 : v); }();   // read per launch: sweeps in one process
+  p.l2_prefetch = (pointwise && p.n_tiles_m >= g_num_sms && a->cin >= 256) ? pf_dist : 0;
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
@@ -636,7 +642,7 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   // CTA pairs for the wide 1x1 convs (fewer operand bytes per SM, the lean epilogue); single CTAs with the fused
   // N = 2*BN MMA (conv_igemm.cuh) for the 3x3 convs and the 64-channel tiles, where they measure 3-15 % faster
   // (profiles/r1_microbench_wide_mma.txt).  DC_CONV_PAIR_ALL=1 restores pairs everywhere.
-  static const bool pair_all = [] { const char* e = getenv("DC_CONV_PAIR_ALL"); return e && e[0] == '1'; }();
+  const bool pair_all = [] { const char* e = getenv("DC_CONV_PAIR_ALL"); return e && e[0] == '1'; }();
   static const bool pair_lean_only = [] { const char* e = getenv("DC_CONV_PAIR_LEAN_ONLY"); return e && e[0] == '1'; }();
   static const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
   const bool lean_shape = lean_on && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res != nullptr && p.ntaps * p.Cin <= 512 && a->cout >= 256;
@@ -652,7 +658,11 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
       if (s <= g_split_k_max.load() && ksteps >= g_split_k_min_steps.load() && units <= (bn == 128 ? max_split_clusters<128>(s) : max_split_clusters<64>(s)) &&
           static_cast<size_t>(units) * (s - 1) * bn * 128 * 4 <= a->splitk_workspace_bytes) { ksplit = s; break; }
   }
-  const bool pair = ksplit == 1 && use_2cta() && !p.swap_ab && g_num_sms >= 2 && (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)));
+  // DC_CONV_PAIR_3X3=1: pairs for the 128-channel-tile 3x3 convs of a throughput-size batch too (A/B switch: 48 instead of 64 KB of operands
+  // per K-step and SM, but three N = 128 MMAs per K-substep instead of the fused N = 256 + N = 128)
+  const bool pair_3x3 = [] { const char* e = getenv("DC_CONV_PAIR_3X3"); return e && e[0] == '1'; }();
+  const bool pair = ksplit == 1 && use_2cta() && !p.swap_ab && g_num_sms >= 2 &&
+                    (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)) || (pair_3x3 && p.ntaps > 1 && bn == 128 && p.n_tiles_m >= g_num_sms));
   // 256-channel tiles for the long-K 1x1 reduce convs (res4 / res5 branch2a): one activation tile against 256 output channels,
   // 2/3 of the operand bytes per MMA; single-buffered accumulators, so only where the K loop (>= 8 K-steps) dwarfs the
   // epilogue and the launch still fills the SMs.  Same per-element K chains as the 128-channel tiles: bitwise the same output.

@@ -10,7 +10,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "deepcut-cnn_b200", "libdeepcut_b200.so")
-OPS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMALDG.*2CTA", "UTMASTG", "LDTM", "UTCBAR", "UTCBAR.*MULTICAST", "UTCATOMSWS", "LDGSTS", "FHFMA", "SYNCS"]
+OPS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMALDG.*2CTA", "UTMASTG", "LDTM", "UTCBAR", "UTCBAR.*MULTICAST", "UTCATOMSWS", "LDGSTS", "FHFMA", "SYNCS", "R2UR.BROADCAST", "ELECT"]
 
 
 def main():
@@ -42,7 +42,10 @@ def main():
     print("| **all kernels** | " + " | ".join(str(tot[o]) for o in OPS) + " |")
     print("\nUTCHMMA = tcgen05.mma kind::f16 (.2CTA = cta_group::2), UTMALDG / UTMASTG = TMA bulk-tensor load / store, LDTM = tcgen05.ld "
           "(TMEM -> registers), UTCBAR = tcgen05.commit (mbarrier arrive, MULTICAST across the CTA pair), LDGSTS = cp.async, "
-          "FHFMA = mixed fp16 x fp16 + fp32 FMA of the epilogue, SYNCS = mbarrier try_wait / arrive.")
+          "FHFMA = mixed fp16 x fp16 + fp32 FMA of the epilogue, SYNCS = mbarrier try_wait / arrive.  R2UR.BROADCAST / ELECT: ptxas's "
+          "per-lane waterfall around a uniform-datapath instruction whose operands it cannot prove warp-uniform (round 1 issued TMA loads "
+          "and MMAs under `lane == 0`: 599 R2UR.BROADCAST in the library; with an elect.sync lane of a converged warp none are left in the "
+          "producer / MMA warps -- the remaining ELECTs are the elect.sync themselves and the epilogue's TMA stores; profiles/r2_issue_lane.md).")
 
 
 if __name__ == "__main__":
