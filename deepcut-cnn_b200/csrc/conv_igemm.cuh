@@ -99,11 +99,6 @@ struct ConvParams {
                             // weight-resident / activation-resident variant of a layer could reach before building it (DC_DEBUG_SKIP)
   int w_evict_last;         // weight tiles are loaded with the L2 evict_last priority (every CTA re-reads them for each of its pixel tiles
                             // while the activations stream through L2: -2 % of the 16x720p step, profiles/r2_chunk_sweep.md)
-  int l2_prefetch;          // > 0: the producer asks L2 for the activation boxes this many K-steps ahead of the one it loads
-                            // (cp.async.bulk.prefetch.tensor, HBM -> L2 only).  The long-K 1x1 reduce convs stream their input from HBM
-                            // exactly once, 128 scattered 128-byte rows per box; the 3-4 stage ring covers ~1.5 us of latency, an HBM
-                            // fetch under load takes longer (the operand-skip microbenchmark: res4 branch2a 81 -> 66 us with no
-                            // activation loads at all, profiles/r2_microbench_bound_elect.txt)
   float* sk_ws;             // split-K scratch: [unit][peer - 1][BN columns][128 rows] fp32 partial tiles (global memory, L2-resident)
 };
 
@@ -254,32 +249,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;
-      // L2 prefetch cursor: walks the same (unit, tap, K-chunk) sequence as the loads, p.l2_prefetch K-steps ahead
-      int pf_unit = unit_first, pf_t = 0, pf_kc = 0, pf_x0 = 0, pf_y0 = 0, pf_img = 0;
-      auto pf_decode = [&]() {
-        if (pf_unit >= total_units) return;
-        int nt_, mt_, tx_, ty_;
-        decode_unit<CG>(p, pf_unit, cta_rank, nt_, mt_, tx_, ty_, pf_img);
-        pf_x0 = tx_ * p.TW * p.in_stride;
-        pf_y0 = ty_ * p.TH * p.in_stride;
-      };
-      auto pf_step = [&]() {          // prefetch the cursor's activation boxes (hi and lo plane), then advance it
-        if (pf_unit >= total_units) return;
-        if (DC_ISSUER_LANE()) {
-          tma_prefetch_l2_5d(&tmA, pf_kc * kBK, pf_x0 + p.tap_dx[pf_t], pf_y0 + p.tap_dy[pf_t], pf_img, 0);
-          tma_prefetch_l2_5d(&tmA, pf_kc * kBK, pf_x0 + p.tap_dx[pf_t], pf_y0 + p.tap_dy[pf_t], pf_img, 1);
-        }
-        __syncwarp();
-        if (++pf_kc == kchunks) {
-          pf_kc = 0;
-          if (++pf_t == p.ntaps) { pf_t = 0; pf_unit += unit_stride; pf_decode(); }
-        }
-      };
-      const bool pf_on = SK == 0 && p.l2_prefetch > 0;
-      if (pf_on) {
-        pf_decode();
-        for (int i = 0; i < p.l2_prefetch; ++i) pf_step();
-      }
       for (int unit = unit_first; unit < total_units; unit += unit_stride) {
         int nt, mt, tx, ty, img;
         decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
@@ -288,7 +257,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int ix = x0 * p.in_stride + p.tap_dx[t], iy = y0 * p.in_stride + p.tap_dy[t];
           for (int kc = 0; kc < kchunks; ++kc) {
             if (SK && (t * kchunks + kc < ks_begin || t * kchunks + kc >= ks_end)) continue;
-            if (pf_on) pf_step();
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             const int kcoord = (t * kchunks + kc) * kBK;

@@ -46,7 +46,6 @@ int g_num_sms = 0;
 // SMs the persistent conv grids leave free (dc_set_reserved_sms): a persistent kernel with one CTA per SM and a static tile schedule
 // cannot share its SMs -- a concurrent NCCL kernel that takes even a few of them delays the CTAs that should have run there by a whole
 // kernel, i.e. doubles that kernel's time.  While a batch exchange is in flight the forwards therefore run on SMs - reserve.
-constexpr int kDefaultL2Prefetch = 0;
 std::atomic<int> g_reserved_sms{[] { const char* e = getenv("DC_RESERVED_SMS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }()};
 int persistent_sms() {
   const int n = g_num_sms - g_reserved_sms.load();
@@ -626,11 +625,6 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   // SMs (a single image) reads each weight tile once, and 251 MB of evict_last lines per forward would only push the activations out
   p.w_evict_last = (a->weights_evict_last && p.n_tiles_m >= g_num_sms) ? 1 : 0;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
-  // HBM -> L2 prefetch distance (K-steps) for launches that stream their activations from HBM once: the stride-1 1x1 convs of a
-  // throughput-size batch (the 3x3 convs re-read theirs from L2, 94 % hit rate; a single image is latency-bound elsewhere).
-  // DC_L2_PREFETCH=<K-steps> overrides, 0 disables.
-  const int pf_dist = [] { const char* e = getenv("DC_L2_PREFETCH"); const int v = e ? atoi(e) : kDefaultL2Prefetch; return v < 0 ? 0 : (v > 64 ? 64 : v); }();   // read per launch: sweeps in one process
-  p.l2_prefetch = (pointwise && p.n_tiles_m >= g_num_sms && a->cin >= 256) ? pf_dist : 0;
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
@@ -639,12 +633,13 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
     // output geometry as the kernel indexes it (flattened for 1x1): [n][out_h][out_w][cout]
     if (int rc = encode_out_map(&to, a->out, n, out_h, out_w, a->cout, p.TW, a->out_plane)) return rc;
   }
-  // CTA pairs for the wide 1x1 convs (fewer operand bytes per SM, the lean epilogue); single CTAs with the fused
-  // N = 2*BN MMA (conv_igemm.cuh) for the 3x3 convs and the 64-channel tiles, where they measure 3-15 % faster
-  // (profiles/r1_microbench_wide_mma.txt).  DC_CONV_PAIR_ALL=1 restores pairs everywhere.
+  // CTA pairs for the 128-channel-tile convs (fewer operand bytes per SM, the lean epilogue); single CTAs with the fused
+  // N = 2*BN MMA (conv_igemm.cuh) for the 64-channel tiles, the head GEMMs and single images, where they measure faster
+  // (profiles/r1_microbench_wide_mma.txt, r2_pairs_3x3_sweep.jsonl).  DC_CONV_PAIR_ALL=1 forces pairs everywhere.
+  // (the A/B switches below are read per launch -- launches happen at graph capture -- so one process can sweep them)
   const bool pair_all = [] { const char* e = getenv("DC_CONV_PAIR_ALL"); return e && e[0] == '1'; }();
   static const bool pair_lean_only = [] { const char* e = getenv("DC_CONV_PAIR_LEAN_ONLY"); return e && e[0] == '1'; }();
-  static const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
+  const bool lean_on = [] { const char* e = getenv("DC_LEAN_EPILOGUE"); return !(e && e[0] == '0'); }();
   const bool lean_shape = lean_on && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res != nullptr && p.ntaps * p.Cin <= 512 && a->cout >= 256;
   // Still fewer units than a quarter / half of the SMs and a K loop worth sharing (>= 16 K-steps; the exchange costs ~4.7 us,
   // a K-step ~0.4 us per CTA, profiles/r1_microbench_latency.txt): split-K clusters of 4 / 2 CTAs per unit.  The summation order over K changes (S partial chains added in rank order), so results differ
@@ -658,16 +653,18 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
       if (s <= g_split_k_max.load() && ksteps >= g_split_k_min_steps.load() && units <= (bn == 128 ? max_split_clusters<128>(s) : max_split_clusters<64>(s)) &&
           static_cast<size_t>(units) * (s - 1) * bn * 128 * 4 <= a->splitk_workspace_bytes) { ksplit = s; break; }
   }
-  // DC_CONV_PAIR_3X3=1: pairs for the 128-channel-tile 3x3 convs of a throughput-size batch too (A/B switch: 48 instead of 64 KB of operands
-  // per K-step and SM, but three N = 128 MMAs per K-substep instead of the fused N = 256 + N = 128)
-  const bool pair_3x3 = [] { const char* e = getenv("DC_CONV_PAIR_3X3"); return e && e[0] == '1'; }();
+  // Pairs for the 128-channel-tile 3x3 convs of a throughput-size batch as well (round 2, after MMA issue stopped being the bottleneck of
+  // the pair kernels, profiles/r2_issue_lane.md): 48 instead of 64 KB of operands per K-step and SM and a fourth pipeline stage; res4 branch2b
+  // 7.15 -> 6.39 ms per step, res3 branch2b 1.61 -> 1.45, res5's dilated 3x3 unchanged (profiles/r2_pairs_3x3_sweep.jsonl).  Bitwise the same
+  // output.  DC_CONV_PAIR_3X3=0 restores single CTAs with the fused N = 2*BN MMA; a single image (fewer pixel tiles than SMs) keeps them.
+  const bool pair_3x3 = [] { const char* e = getenv("DC_CONV_PAIR_3X3"); return !(e && e[0] == '0'); }();
   const bool pair = ksplit == 1 && use_2cta() && !p.swap_ab && g_num_sms >= 2 &&
                     (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)) || (pair_3x3 && p.ntaps > 1 && bn == 128 && p.n_tiles_m >= g_num_sms));
   // 256-channel tiles for the long-K 1x1 reduce convs (res4 / res5 branch2a): one activation tile against 256 output channels,
   // 2/3 of the operand bytes per MMA; single-buffered accumulators, so only where the K loop (>= 8 K-steps) dwarfs the
   // epilogue and the launch still fills the SMs.  Same per-element K chains as the 128-channel tiles: bitwise the same output.
   // DC_CONV_BN256=0 disables.
-  static const bool bn256_on = [] { const char* e = getenv("DC_CONV_BN256"); return !(e && e[0] == '0'); }();
+  const bool bn256_on = [] { const char* e = getenv("DC_CONV_BN256"); return !(e && e[0] == '0'); }();
   // Measured (profiles/r2_ncu_summary.md): a 256-channel unit costs ~1.8x a 128-channel one (-7..10 % per unit of work), so the wider
   // tile only wins when it does not cost a wave: res5 branch2a at 16x720p (450 units on 74 CTA pairs: 7 rounds x 1.8 < 13) takes it,
   // res4 branch2a (225 units = 3.04 waves -> 4 rounds x 1.8 > 7) does not.
@@ -676,8 +673,8 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   if (wide256) {
     const long long pairs = persistent_sms() / 2, mp = (p.n_tiles_m + 1) / 2;
     const long long rounds128 = (mp * (rows / 128) + pairs - 1) / pairs, rounds256 = (mp * (rows / 256) + pairs - 1) / pairs;
-    static const bool force = [] { const char* e = getenv("DC_CONV_BN256"); return e && e[0] == '2'; }();      // 2 = wherever legal (A/B runs)
-    wide256 = force ? mp * (rows / 256) >= pairs : (rounds256 * 18 < rounds128 * 10 && mp * (rows / 256) >= pairs);
+    const bool force = [] { const char* e = getenv("DC_CONV_BN256"); return e && e[0] == '2'; }();      // 2 = wherever legal (A/B runs)
+    wide256 = force ? mp * (rows / 256) >= pairs : (p.ntaps == 1 && rounds256 * 18 < rounds128 * 10 && mp * (rows / 256) >= pairs);
   }
   if (wide256) { bn = 256; p.n_tiles_n = rows / 256; }
   if (int rc = encode_w_map(&tb, a->w_packed, rows, static_cast<long long>(p.ntaps) * a->cin, pair ? bn / 2 : bn)) return rc;

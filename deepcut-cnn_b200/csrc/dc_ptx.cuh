@@ -103,13 +103,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// HBM -> L2 prefetch of one box of a tensor map (no shared-memory destination, no completion tracking): UTMAPF.L2
-__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-
 // ---- 2-CTA (cta_group::2) variants: both CTAs of a pair load, the transaction bytes land on the
 // LEADER's (even CTA) mbarrier: clearing bit 24 of a shared::cta address names the same offset in
 // the pair's even CTA within the shared::cluster window.
