@@ -625,6 +625,12 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   // SMs (a single image) reads each weight tile once, and 251 MB of evict_last lines per forward would only push the activations out
   p.w_evict_last = (a->weights_evict_last && p.n_tiles_m >= g_num_sms) ? 1 : 0;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
+  // A/B switch (read per launch): DC_OUT_KEEP_MB=<MiB> pins that much of every residual-block output larger than it in L2 (see ConvParams)
+  {
+    const char* e = getenv("DC_OUT_KEEP_MB");
+    const double keep = e ? atof(e) * 1048576.0 : 0.0, bytes = 4.0 * static_cast<double>(out_elems);
+    p.out_keep_frac = (keep > 0 && a->residual != nullptr && p.n_tiles_m >= g_num_sms && bytes > keep) ? static_cast<float>(keep / bytes) : 0.f;
+  }
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
@@ -660,14 +666,13 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   const bool pair_3x3 = [] { const char* e = getenv("DC_CONV_PAIR_3X3"); return !(e && e[0] == '0'); }();
   const bool pair = ksplit == 1 && use_2cta() && !p.swap_ab && g_num_sms >= 2 &&
                     (pair_all || (p.ntaps == 1 && bn == 128 && (!pair_lean_only || lean_shape)) || (pair_3x3 && p.ntaps > 1 && bn == 128 && p.n_tiles_m >= g_num_sms));
-  // 256-channel tiles for the long-K 1x1 reduce convs (res4 / res5 branch2a): one activation tile against 256 output channels,
-  // 2/3 of the operand bytes per MMA; single-buffered accumulators, so only where the K loop (>= 8 K-steps) dwarfs the
-  // epilogue and the launch still fills the SMs.  Same per-element K chains as the 128-channel tiles: bitwise the same output.
-  // DC_CONV_BN256=0 disables.
-  const bool bn256_on = [] { const char* e = getenv("DC_CONV_BN256"); return !(e && e[0] == '0'); }();
-  // Measured (profiles/r2_ncu_summary.md): a 256-channel unit costs ~1.8x a 128-channel one (-7..10 % per unit of work), so the wider
-  // tile only wins when it does not cost a wave: res5 branch2a at 16x720p (450 units on 74 CTA pairs: 7 rounds x 1.8 < 13) takes it,
-  // res4 branch2a (225 units = 3.04 waves -> 4 rounds x 1.8 > 7) does not.
+  // 256-channel tiles (conv_igemm<256, 2, 8>: one activation tile against 256 output channels, 2/3 of the operand bytes per MMA,
+  // single-buffered accumulators; same per-element K chains: bitwise the same output).  While every MMA of the pair kernels sat in
+  // ptxas's issue waterfall the wide tile's half as many, twice as long MMAs were worth 7-10 % per unit of work and it was taken
+  // wherever it did not cost a wave (res5 branch2a, the projection shortcuts).  With the elect.sync issue path the 128-channel tiles are
+  // faster there too (16 x 720p: res5 branch2a 0.87 -> 0.74 ms, res4 / res5 branch1 0.24 / 0.68 -> 0.18 / 0.57 ms per step,
+  // profiles/r2_tile_choice_sweep.jsonl), so it is OFF by default: DC_CONV_BN256=1 = where it costs no wave, 2 = wherever legal.
+  const bool bn256_on = [] { const char* e = getenv("DC_CONV_BN256"); return e && (e[0] == '1' || e[0] == '2'); }();
   bool wide256 = bn256_on && pair && !lean_shape && bn == 128 && p.out_mode == dc::kOutSplitNHWC && p.res == nullptr && rows % 256 == 0 &&
                  p.ntaps * (a->cin / dc::kBK) >= 8;
   if (wide256) {

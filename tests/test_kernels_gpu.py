@@ -50,6 +50,11 @@ CONV_CASES = [
     # accumulators): res4 branch2a (one 256-channel tile) and res5 branch2a (two), 45x80 maps with a ragged last pixel tile
     (1024, 256, 1, 0, 1, 45, 80, 6),
     (2048, 512, 1, 0, 1, 45, 83, 3),
+    # 3x3 convs with at least as many pixel tiles as SMs: the CTA-pair form of the 128-channel-tile 3x3 kernel (two vertically
+    # adjacent 16x8 tiles per pair, 45 rows = ragged last pair, odd tile counts = a phantom tile in the last pair)
+    (256, 256, 3, 1, 1, 45, 80, 6),
+    (512, 512, 3, 2, 2, 45, 80, 5),
+    (128, 128, 3, 1, 1, 37, 83, 9),
 ]
 
 
@@ -67,6 +72,23 @@ def test_conv_bn_relu_matches_oracle(case, _gpu):
     assert got.shape == ref.shape
     assert np.isfinite(got).all()
     assert np.abs(got - ref).max() < 1e-4, np.abs(got - ref).max()
+
+
+@pytest.mark.parametrize("case", [(1024, 256, 1, 0, 1, 45, 80, 6), (2048, 512, 1, 0, 1, 45, 83, 3), (256, 256, 3, 1, 1, 45, 80, 6), (512, 512, 3, 2, 2, 45, 80, 5)])
+def test_tile_and_pairing_choices_are_bitwise_neutral(case, _gpu, monkeypatch):
+    """dc_conv_forward's tile choices (CTA pairs or single CTAs for the 3x3 convs, 128- or 256-channel tiles; off-by-default forms
+    included) keep every output element's K chain: the same launch under each switch gives bitwise the same tensor."""
+    ci, co, k, pad, dil, h, w, n = case
+    rng = np.random.default_rng(ci + co + k)
+    x = np.maximum(rng.standard_normal((n, ci, h, w)), 0).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, k, k)) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32)
+    a, b = _bn_params(rng, co)
+    base = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True)
+    for var, val in (("DC_CONV_BN256", "2"), ("DC_CONV_PAIR_3X3", "0"), ("DC_CONV_PAIR_ALL", "1")):
+        monkeypatch.setenv(var, val)
+        got = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True)
+        monkeypatch.delenv(var)
+        assert np.array_equal(got, base), (var, float(np.abs(got - base).max()))
 
 
 def test_conv_residual_add_relu(_gpu):
