@@ -99,9 +99,6 @@ struct ConvParams {
                             // weight-resident / activation-resident variant of a layer could reach before building it (DC_DEBUG_SKIP)
   int w_evict_last;         // weight tiles are loaded with the L2 evict_last priority (every CTA re-reads them for each of its pixel tiles
                             // while the activations stream through L2: -2 % of the 16x720p step, profiles/r2_chunk_sweep.md)
-  float out_keep_frac;      // lean epilogue: > 0 = this fraction of the output's lines is written with the L2 evict_last priority (a block
-                            // output larger than L2 is re-read twice by the next block -- as its input and as its shortcut; LRU would
-                            // stream all of it through, a pinned subset stays)
   float* sk_ws;             // split-K scratch: [unit][peer - 1][BN columns][128 rows] fp32 partial tiles (global memory, L2-resident)
 };
 
@@ -414,8 +411,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       cp_async_commit();
     };
     if (has_res) issue_residual(unit_first);
-    const bool keep = p.out_keep_frac > 0.f;
-    const uint64_t pol_out = keep ? l2_policy_keep_fraction(p.out_keep_frac) : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = unit_first; unit < total_units; unit += unit_stride) {
@@ -493,13 +488,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
           const int r0 = q * 32;
           const int box_x = tx * p.TW + (r0 & (p.TW - 1)), box_y = ty * p.TH + (r0 >> p.log2_tw);
-          if (keep) {
-            tma_store_5d_hint(&tmO, stg, n0 + c0, box_x, box_y, img, 0, pol_out);
-            tma_store_5d_hint(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1, pol_out);
-          } else {
-            tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
-            tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
-          }
+          tma_store_5d(&tmO, stg, n0 + c0, box_x, box_y, img, 0);
+          tma_store_5d(&tmO, stg + 2048, n0 + c0, box_x, box_y, img, 1);
           tma_store_commit();
           tma_store_wait_read();                                  // staging tile drained: safe to refill
         }

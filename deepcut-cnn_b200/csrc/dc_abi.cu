@@ -625,12 +625,6 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   // SMs (a single image) reads each weight tile once, and 251 MB of evict_last lines per forward would only push the activations out
   p.w_evict_last = (a->weights_evict_last && p.n_tiles_m >= g_num_sms) ? 1 : 0;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
-  // A/B switch (read per launch): DC_OUT_KEEP_MB=<MiB> pins that much of every residual-block output larger than it in L2 (see ConvParams)
-  {
-    const char* e = getenv("DC_OUT_KEEP_MB");
-    const double keep = e ? atof(e) * 1048576.0 : 0.0, bytes = 4.0 * static_cast<double>(out_elems);
-    p.out_keep_frac = (keep > 0 && a->residual != nullptr && p.n_tiles_m >= g_num_sms && bytes > keep) ? static_cast<float>(keep / bytes) : 0.f;
-  }
 
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));

@@ -176,21 +176,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
       "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-// the same store with an L2 eviction-priority hint for the lines it writes
-__device__ __forceinline__ void tma_store_5d_hint(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;" ::"l"(
-          reinterpret_cast<uint64_t>(m)),
-      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
-      : "memory");
-}
-// evict_last for `fraction` of the lines touched (chosen by address hash), unchanged priority for the rest: pins a fixed subset of a
-// tensor that is larger than L2 instead of letting LRU stream all of it through
-__device__ __forceinline__ uint64_t l2_policy_keep_fraction(float fraction) {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, %1;" : "=l"(p) : "f"(fraction));
-  return p;
-}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all prior bulk groups of this thread have finished READING shared memory (safe to overwrite it)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
