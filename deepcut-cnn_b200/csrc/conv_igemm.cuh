@@ -99,6 +99,17 @@ struct ConvParams {
                             // weight-resident / activation-resident variant of a layer could reach before building it (DC_DEBUG_SKIP)
   int w_evict_last;         // weight tiles are loaded with the L2 evict_last priority (every CTA re-reads them for each of its pixel tiles
                             // while the activations stream through L2: -2 % of the 16x720p step, profiles/r2_chunk_sweep.md)
+  // TALL mode (conv_igemm_kernel<64, 2, 8, 0, 1>: 64 -> 64 channel convs whose taps differ mostly in dy -- res2's 3x3 convs, the stem's
+  // four vertical taps): the taps are grouped by column offset; per group ONE box of tall_rows = TH + (taps_per_group - 1) * row_step
+  // input rows is loaded and every tap of the group is the same shared-memory tile read from a row offset (a multiple of 1024 bytes,
+  // so the 128-byte-swizzle phase is unchanged); all weight tiles stay resident in shared memory.
+  int tall_groups;          // tap groups (distinct dx): 3 for a 3x3, 1 for the stem
+  int tall_taps_per_group;  // tap (g, i) = packed K block g + i * tall_groups
+  int tall_gdx[3];          // input column offset of each group
+  int tall_top;             // input row of the box's first row relative to the tile's first output row
+  int tall_plane_bytes;     // one plane of a box: tall_rows * TW * 128
+  int tall_tap_bytes;       // shared-memory distance between consecutive taps of a group: row_step * TW * 128
+  int tall_stages;          // boxes in flight (2..4)
   float* sk_ws;             // split-K scratch: [unit][peer - 1][BN columns][128 rows] fp32 partial tiles (global memory, L2-resident)
 };
 
@@ -127,6 +138,9 @@ struct ConvCfg {
   static constexpr int kTmemCols = 2 * BN * kAccBufs;              // kAccBufs x (main, cross)
   static constexpr int kStagingBytes = EW * 4096;        // per epilogue warp: [32 px][32 ch] fp16 x {hi, lo}
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // TALL mode: box ring + resident weights share what one CTA can have (same launch size as the four-stage pair kernel)
+  static constexpr int kTallOperandBytes = 192 * 1024;
+  static constexpr int kTallSmemBytes = kTallOperandBytes + kStagingBytes + 1024 + 256;
 };
 
 // SK = 1 ("split-K", the latency regime: fewer work units than SMs): a cluster of S = 2 or 4 CTAs shares ONE unit,
@@ -149,12 +163,13 @@ __device__ __forceinline__ void decode_unit(const ConvParams& p, int unit, int c
   fastdivmod(p.div_ty, rest, img, ty);
 }
 
-template <int BN, int CG, int EW, int SK = 0>
+template <int BN, int CG, int EW, int SK = 0, int TALL = 0>
 __global__ void __launch_bounds__(conv_threads(EW), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = ConvCfg<BN, CG, EW>;
   static_assert(SK == 0 || (CG == 1 && EW == 8), "split-K runs on single CTAs with the 8-warp epilogue");
+  static_assert(TALL == 0 || (BN == 64 && CG == 2 && EW == 8 && SK == 0), "TALL: 64-channel tiles, CTA pairs, 8-warp epilogue");
   const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int ksplit = SK ? static_cast<int>(cluster_nctarank()) : 1;
   const int krank = SK ? static_cast<int>(cluster_ctarank()) : 0;
@@ -166,7 +181,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* staging_all = smem + kStages * Cfg::kStageBytes;
+  uint8_t* staging_all = smem + (TALL ? Cfg::kTallOperandBytes : kStages * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging_all + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
@@ -197,6 +212,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (SK) {
       mbar_init(red_full, static_cast<uint32_t>(ksplit - 1));
     }
+    if (TALL) mbar_init(red_full, 1);          // TALL: "resident weights have landed" (the slot split-K uses otherwise)
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -219,7 +235,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // that the operands of the uniform-datapath instructions (UTMALDG here, UTCHMMA / UTCBAR in the MMA warp) are warp-uniform and
     // wraps every one of them in a per-lane waterfall (ELECT, four or five R2UR.BROADCAST, two PLOP3, a back branch: ~14 SASS
     // instructions per instruction issued); inside an elect.sync region of converged code they are plain uniform-register operands.
-    {
+    if constexpr (TALL != 0) {
+      const uint64_t pol_w = l2_policy(p.w_evict_last ? 2 : 0);
+      const uint32_t plane_bytes = static_cast<uint32_t>(p.tall_plane_bytes), stage_bytes = 2u * plane_bytes;
+      const int nst = p.tall_stages;
+      uint8_t* bres = smem + nst * stage_bytes;                   // [tap][plane][32 rows][128 B]
+      // every weight tile of the layer, once per CTA, before griddepcontrol.wait (weights do not depend on the predecessor)
+      if (DC_ISSUER_LANE()) {
+        if (cta_rank == 0) mbar_expect_tx(red_full, 2u * static_cast<uint32_t>(p.ntaps) * 2u * Cfg::kBBytes);
+        for (int t = 0; t < p.ntaps; ++t) {
+          tma_load_3d_2cta(bres + (2 * t) * Cfg::kBBytes, &tmB, red_full, t * kBK, cta_rank * Cfg::kBRows, 0, pol_w);
+          tma_load_3d_2cta(bres + (2 * t + 1) * Cfg::kBBytes, &tmB, red_full, t * kBK, cta_rank * Cfg::kBRows, 1, pol_w);
+        }
+      }
+      __syncwarp();
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+        int nt, mt, tx, ty, img;
+        decode_unit<CG>(p, unit, cta_rank, nt, mt, tx, ty, img);
+        const int x0 = tx * p.TW, y0 = ty * p.TH + p.tall_top;
+        for (int g = 0; g < p.tall_groups; ++g) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (DC_ISSUER_LANE()) {
+            uint8_t* sa = smem + stage * stage_bytes;
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);      // both CTAs' boxes, both planes
+            tma_load_5d_2cta(sa, &tmA, &full_bar[stage], 0, x0 + p.tall_gdx[g], y0, img, 0);
+            tma_load_5d_2cta(sa + plane_bytes, &tmA, &full_bar[stage], 0, x0 + p.tall_gdx[g], y0, img, 1);
+          }
+          __syncwarp();
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
       const uint64_t pol_w = l2_policy(p.w_evict_last ? 2 : 0);
       // Weights do not depend on the predecessor kernel: the weight tiles of this CTA's first K-steps (one per pipeline
       // stage) are requested BEFORE griddepcontrol.wait, so their HBM latency (a single image re-reads all 251 MB of
@@ -327,6 +376,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (TALL != 0) {
+        const uint32_t plane_bytes = static_cast<uint32_t>(p.tall_plane_bytes), stage_bytes = 2u * plane_bytes;
+        const int nst = p.tall_stages;
+        const uint32_t bres = smem_u32(smem + nst * stage_bytes);
+        mbar_wait(red_full, 0);                       // the resident weight tiles have landed (both CTAs')
+        tc_fence_after();
+        for (int unit = unit_first; unit < total_units; unit += unit_stride) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 2 * BN);
+          const uint32_t dx = d + BN;
+          for (int g = 0; g < p.tall_groups; ++g) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+            if (DC_ISSUER_LANE()) {
+              for (int i = 0; i < p.tall_taps_per_group; ++i) {
+                const int tap = g + i * p.tall_groups;
+                const uint32_t aoff = static_cast<uint32_t>(i * p.tall_tap_bytes);      // a multiple of 1024: same swizzle phase
+                const uint64_t a_hi = umma_desc_k_sw128(sa + aoff);
+                const uint64_t a_lo = umma_desc_k_sw128(sa + plane_bytes + aoff);
+                const uint64_t b_hi = umma_desc_k_sw128(bres + static_cast<uint32_t>(2 * tap) * Cfg::kBBytes);
+                const uint64_t b_lo = umma_desc_k_sw128(bres + static_cast<uint32_t>(2 * tap + 1) * Cfg::kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);
+                  const uint32_t accum = (g | i | k) != 0 ? 1u : 0u;          // the unit's first MMAs overwrite the accumulators
+                  umma_f16_2cta(d, a_hi + adv, b_hi + adv, idesc, accum);
+                  umma_f16_2cta(dx, a_hi + adv, b_lo + adv, idesc, accum);
+                  umma_f16_2cta(dx, a_lo + adv, b_hi + adv, idesc, 1);
+                }
+              }
+              umma_commit_2cta(&empty_bar[stage]);
+              if (g + 1 == p.tall_groups) umma_commit_2cta(&tfull_bar[acc]);
+            }
+            __syncwarp();
+            if (++stage == nst) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == Cfg::kAccBufs) { acc = 0; acc_phase ^= 1; }
+        }
+      } else
       for (int unit = unit_first; unit < total_units; unit += unit_stride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();

@@ -179,7 +179,7 @@ bool use_pdl() {
 }
 
 // ksplit > 1 (SK = 1): a cluster of `ksplit` CTAs per work unit, each taking a share of the K loop (conv_igemm.cuh)
-template <int BN, int CG, int EW = 8, int SK = 0>
+template <int BN, int CG, int EW = 8, int SK = 0, int TALL = 0>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const dc::ConvParams& p, cudaStream_t st,
                 int ksplit = 1) {
   const int units = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
@@ -195,7 +195,7 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(dc::conv_threads(EW));
-  cfg.dynamicSmemBytes = dc::ConvCfg<BN, CG, EW>::kSmemBytes;
+  cfg.dynamicSmemBytes = TALL ? dc::ConvCfg<BN, CG, EW>::kTallSmemBytes : dc::ConvCfg<BN, CG, EW>::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;
@@ -213,10 +213,50 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG, EW, SK>, ta, tb, to, pk));
+  DC_CUDA(cudaLaunchKernelEx(&cfg, dc::conv_igemm_kernel<BN, CG, EW, SK, TALL>, ta, tb, to, pk));
   g_launches++;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
+}
+
+// TALL-mode geometry (conv_igemm.cuh) for the tile rectangle already chosen in `p`: `groups` column offsets `gdx`, `taps_per_group`
+// taps each, `row_step` input rows apart, the first one `top` rows from the tile's first output row.  False when the boxes do not fit
+// the shared-memory budget or the tap offsets would break the 1024-byte swizzle phase.
+bool setup_tall(dc::ConvParams& p, int groups, int taps_per_group, const int* gdx, int top, int row_step, int* tall_rows_out) {
+  const int tall_rows = p.TH + (taps_per_group - 1) * row_step;
+  if (tall_rows > 256 || (p.TW * row_step) % 8 != 0 || (p.TW * tall_rows) % 8 != 0 || groups > 3) return false;
+  const long long plane = static_cast<long long>(tall_rows) * p.TW * 128;
+  const long long avail = dc::ConvCfg<64, 2, 8>::kTallOperandBytes - static_cast<long long>(p.ntaps) * 2 * dc::ConvCfg<64, 2, 8>::kBBytes;
+  long long stages = avail / (2 * plane);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return false;
+  p.tall_groups = groups;
+  p.tall_taps_per_group = taps_per_group;
+  for (int g = 0; g < groups; ++g) p.tall_gdx[g] = gdx[g];
+  p.tall_top = top;
+  p.tall_plane_bytes = static_cast<int>(plane);
+  p.tall_tap_bytes = row_step * p.TW * 128;
+  p.tall_stages = static_cast<int>(stages);
+  *tall_rows_out = tall_rows;
+  return true;
+}
+// the tile rectangles TALL mode chooses from: at least 8 rows, so that a box of TH + (taps - 1) * row_step rows does not dwarf the tile
+void choose_tall_tile(dc::ConvParams& p, int n, int out_h, int out_w) {
+  const int cand[2][2] = {{16, 8}, {8, 16}};
+  long long best = -1;
+  for (int i = 0; i < 2; ++i) {
+    const int tw = cand[i][0], th = cand[i][1];
+    const long long area = static_cast<long long>((out_w + tw - 1) / tw) * tw * ((out_h + th - 1) / th) * th;
+    if (best < 0 || area < best) { best = area; p.TW = tw; p.TH = th; }
+  }
+  for (p.log2_tw = 0; (1 << p.log2_tw) < p.TW; ++p.log2_tw) {}
+  p.tiles_x = (out_w + p.TW - 1) / p.TW;
+  p.tiles_y = (out_h + p.TH - 1) / p.TH;
+  p.n_tiles_m = n * p.tiles_x * p.tiles_y;
+}
+bool use_tall() {        // read per launch (graph capture time): one process can sweep it
+  const char* e = getenv("DC_CONV_TALL");
+  return !(e && e[0] == '0');
 }
 
 // How many split-K clusters of `s` CTAs (one CTA per SM: ~224 KB of shared memory each) the device keeps resident at once:
@@ -323,6 +363,7 @@ int dc_init(int device) {
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 2, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 2, 16>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<256, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<256, 2, 8>::kSmemBytes));
+  DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 2, 8, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 2, 8>::kTallSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<128, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<128, 1, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv_igemm_kernel<64, 1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::ConvCfg<64, 1, 8>::kSmemBytes));
   DC_CUDA(cudaFuncSetAttribute(dc::conv1_7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::kC1SmemFloats * 4));
@@ -626,6 +667,25 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   p.w_evict_last = (a->weights_evict_last && p.n_tiles_m >= g_num_sms) ? 1 : 0;
   p.sk_ws = static_cast<float*>(a->splitk_workspace);
 
+  // 64 -> 64 channel 3x3 convs of a throughput-size batch (res2's branch2b): TALL mode -- one tall activation box per column offset
+  // instead of one box per tap, all nine weight tiles resident in shared memory (conv_igemm.cuh).  These layers were bound by L2 -> SM
+  // operand traffic (48 KB per 384 MMA cycles); the boxes are a third of those bytes.  Same K order per output element: bitwise the
+  // same result.  DC_CONV_TALL=0 disables.
+  if (use_tall() && a->kh == 3 && a->kw == 3 && stride == 1 && a->pad == a->dilation && a->cin == 64 && rows == 64 && !a->out_f32_rows &&
+      use_2cta() && g_num_sms >= 2) {
+    dc::ConvParams pt = p;
+    choose_tall_tile(pt, n, out_h, out_w);
+    const int gdx[3] = {-a->pad, -a->pad + a->dilation, -a->pad + 2 * a->dilation};
+    int tall_rows = 0;
+    if (pt.n_tiles_m >= g_num_sms && setup_tall(pt, 3, 3, gdx, -a->pad, a->dilation, &tall_rows)) {
+      pt.n_tiles_n = 1;
+      CUtensorMap tta, ttb, tto;
+      if (int rc = encode_act_map(&tta, a->x, n, h, w, a->cin, pt.TW, tall_rows, 1, a->x_plane)) return rc;
+      if (int rc = encode_out_map(&tto, a->out, n, out_h, out_w, a->cout, pt.TW, a->out_plane)) return rc;
+      if (int rc = encode_w_map(&ttb, a->w_packed, rows, static_cast<long long>(pt.ntaps) * a->cin, 32)) return rc;
+      return launch_conv<64, 2, 8, 0, 1>(tta, ttb, tto, pt, static_cast<cudaStream_t>(stream));
+    }
+  }
   CUtensorMap ta, tb, to;
   memset(&to, 0, sizeof(to));
   if (int rc = encode_act_map(&ta, a->x, n, h, w, a->cin, p.TW, p.TH, stride, a->x_plane)) return rc;
@@ -724,21 +784,33 @@ int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packe
   p.out_mode = dc::kOutSplitNHWC;
   p.early_weights = use_early_weights();
 
+  // TALL mode (conv_igemm.cuh): the four taps are the same 4-pixel windows one row apart -- one box of TH + 3 rows per tile instead of
+  // four boxes of TH rows, the four weight tiles resident in shared memory.  DC_CONV_TALL=0 disables.
+  bool tall = false;
+  int box_rows = p.TH;
+  if (use_tall() && use_2cta() && g_num_sms >= 2) {
+    dc::ConvParams pt = p;
+    choose_tall_tile(pt, n, h2, w2);
+    const int gdx[1] = {0};
+    int tall_rows = 0;
+    if (pt.n_tiles_m >= g_num_sms && setup_tall(pt, 1, 4, gdx, -2, 1, &tall_rows)) { p = pt; box_rows = tall_rows; tall = true; }
+  }
   // A: overlapping 4-pixel windows of the padded space-to-depth image (W stride = one 16-channel pixel)
   CUtensorMap ta, tb, to;
   {
     const cuuint64_t dims[5] = {64, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)n, 2};
     const cuuint64_t strides[4] = {32, (cuuint64_t)wp * 32, (cuuint64_t)h2 * wp * 32, (cuuint64_t)plane * 2};
-    const cuuint32_t box[5] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1, 1};
+    const cuuint32_t box[5] = {64, (cuuint32_t)p.TW, (cuuint32_t)box_rows, 1, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, workspace, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DC_ERR_CUDA, "cuTensorMapEncodeTiled(stem windows) failed: %d", (int)r);
   }
   static const bool pair_all = [] { const char* e = getenv("DC_CONV_PAIR_ALL"); return e && e[0] == '1'; }();
-  const bool pair = use_2cta() && g_num_sms >= 2 && pair_all;       // BN = 64: single CTAs + fused wide MMA
+  const bool pair = tall || (use_2cta() && g_num_sms >= 2 && pair_all);       // BN = 64 otherwise: single CTAs + fused wide MMA
   if (int rc = encode_w_map(&tb, w_packed, 64, 256, pair ? 32 : 64)) return rc;
   if (int rc = encode_out_map(&to, out, n, h2, w2, 64, p.TW)) return rc;
+  if (tall) return launch_conv<64, 2, 8, 0, 1>(ta, tb, to, p, st);
   return pair ? launch_conv<64, 2>(ta, tb, to, p, st) : launch_conv<64, 1>(ta, tb, to, p, st);
 }
 

@@ -55,6 +55,11 @@ CONV_CASES = [
     (256, 256, 3, 1, 1, 45, 80, 6),
     (512, 512, 3, 2, 2, 45, 80, 5),
     (128, 128, 3, 1, 1, 37, 83, 9),
+    # 64 -> 64 channel 3x3 convs with at least as many 16x8 tiles as SMs: TALL mode (one tall box per column offset, resident weights),
+    # ragged in both directions, dilation 1 and 2, an odd tile count (phantom tile in the last pair)
+    (64, 64, 3, 1, 1, 45, 83, 6),
+    (64, 64, 3, 2, 2, 41, 70, 7),
+    (64, 48, 3, 1, 1, 60, 100, 3),
 ]
 
 
@@ -74,7 +79,8 @@ def test_conv_bn_relu_matches_oracle(case, _gpu):
     assert np.abs(got - ref).max() < 1e-4, np.abs(got - ref).max()
 
 
-@pytest.mark.parametrize("case", [(1024, 256, 1, 0, 1, 45, 80, 6), (2048, 512, 1, 0, 1, 45, 83, 3), (256, 256, 3, 1, 1, 45, 80, 6), (512, 512, 3, 2, 2, 45, 80, 5)])
+@pytest.mark.parametrize("case", [(1024, 256, 1, 0, 1, 45, 80, 6), (2048, 512, 1, 0, 1, 45, 83, 3), (256, 256, 3, 1, 1, 45, 80, 6), (512, 512, 3, 2, 2, 45, 80, 5),
+                                  (64, 64, 3, 1, 1, 45, 83, 6), (64, 64, 3, 2, 2, 41, 70, 7)])
 def test_tile_and_pairing_choices_are_bitwise_neutral(case, _gpu, monkeypatch):
     """dc_conv_forward's tile choices (CTA pairs or single CTAs for the 3x3 convs, 128- or 256-channel tiles; off-by-default forms
     included) keep every output element's K chain: the same launch under each switch gives bitwise the same tensor."""
@@ -84,7 +90,7 @@ def test_tile_and_pairing_choices_are_bitwise_neutral(case, _gpu, monkeypatch):
     wt = (rng.standard_normal((co, ci, k, k)) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32)
     a, b = _bn_params(rng, co)
     base = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True)
-    for var, val in (("DC_CONV_BN256", "2"), ("DC_CONV_PAIR_3X3", "0"), ("DC_CONV_PAIR_ALL", "1")):
+    for var, val in (("DC_CONV_BN256", "2"), ("DC_CONV_PAIR_3X3", "0"), ("DC_CONV_PAIR_ALL", "1"), ("DC_CONV_TALL", "0")):
         monkeypatch.setenv(var, val)
         got = _gpu.conv_bn(x, wt, a, b, pad=pad, dil=dil, relu=True)
         monkeypatch.delenv(var)
@@ -251,7 +257,7 @@ def test_conv1_stem_tensor_core(_gpu):
     """dc_conv1_tc_forward: space-to-depth + overlapping-window tensor map + tcgen05 conv, vs the oracle."""
     L = libdc.lib()
     rng = np.random.default_rng(14)
-    for (n, h, w) in ((1, 64, 64), (2, 75, 101), (1, 720, 1280)):
+    for (n, h, w) in ((1, 64, 64), (2, 75, 101), (3, 150, 230), (1, 720, 1280)):      # the last two: enough tiles for TALL mode
         x = dcutil.synth.images(n, h, w, seed=3)
         wt = (rng.standard_normal((64, 3, 7, 7)) * np.sqrt(2.0 / 147)).astype(np.float32)
         a, b = _bn_params(rng, 64)
