@@ -76,6 +76,10 @@ struct ConvParams {
   int ntaps;
   int tap_dy[kMaxTaps];     // input row/col offset of each tap relative to the output pixel
   int tap_dx[kMaxTaps];
+  int tap_kblk[kMaxTaps];   // which Cin-wide block of the packed K axis holds tap t's weights.  Identity except for the 64 -> 64 channel
+                            // 3x3 convs, whose taps are visited column offset by column offset -- the order TALL mode needs -- so that the
+                            // plain kernel (small launches) and the TALL kernel (throughput launches) add every output element's products
+                            // in the same order: the result stays bitwise independent of the batch size
   int TH, TW;               // tile rectangle, TH * TW == 128 (TW a power of two)
   int log2_tw;
   int tiles_x, tiles_y;     // per image
@@ -104,7 +108,7 @@ struct ConvParams {
   // input rows is loaded and every tap of the group is the same shared-memory tile read from a row offset (a multiple of 1024 bytes,
   // so the 128-byte-swizzle phase is unchanged); all weight tiles stay resident in shared memory.
   int tall_groups;          // tap groups (distinct dx): 3 for a 3x3, 1 for the stem
-  int tall_taps_per_group;  // tap (g, i) = packed K block g + i * tall_groups
+  int tall_taps_per_group;  // the taps are visited group by group: visiting position g * taps_per_group + i (tap_dy / tap_dx / tap_kblk are in that order)
   int tall_gdx[3];          // input column offset of each group
   int tall_top;             // input row of the box's first row relative to the tile's first output row
   int tall_plane_bytes;     // one plane of a box: tall_rows * TW * 128
@@ -280,15 +284,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int n0 = nt0 * BN + cta_rank * Cfg::kBRows;
         for (int ks = ks_begin; ks < ks_end && npre < kStages; ++ks, ++npre) {
           uint8_t* sa = smem + npre * Cfg::kStageBytes;
+          const int kcoord0 = (p.tap_kblk[ks / kchunks] * kchunks + ks % kchunks) * kBK;
           if (DC_ISSUER_LANE()) {
             if (CG == 2) {
               if (cta_rank == 0) mbar_expect_tx(&full_bar[npre], 2 * Cfg::kStageBytes);
-              tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
-              tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
+              tma_load_3d_2cta(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], kcoord0, n0, 0, pol_w);
+              tma_load_3d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], kcoord0, n0, 1, pol_w);
             } else {
               mbar_expect_tx(&full_bar[npre], Cfg::kStageBytes);
-              tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], ks * kBK, n0, 0, pol_w);
-              tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], ks * kBK, n0, 1, pol_w);
+              tma_load_3d(sa + 2 * Cfg::kABytes, &tmB, &full_bar[npre], kcoord0, n0, 0, pol_w);
+              tma_load_3d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full_bar[npre], kcoord0, n0, 1, pol_w);
             }
           }
           __syncwarp();
@@ -308,7 +313,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (SK && (t * kchunks + kc < ks_begin || t * kchunks + kc >= ks_end)) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            const int kcoord = (t * kchunks + kc) * kBK;
+            const int kcoord = (p.tap_kblk[t] * kchunks + kc) * kBK;
             const bool fresh = issued >= npre;      // else: this stage's barrier is armed and its weight tiles are on their way
             if (SK == 0 && p.debug_skip && issued >= kStages) {
               // microbenchmark mode: arm the barrier for exactly what is still loaded
@@ -393,7 +398,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t sa = smem_u32(smem + stage * stage_bytes);
             if (DC_ISSUER_LANE()) {
               for (int i = 0; i < p.tall_taps_per_group; ++i) {
-                const int tap = g + i * p.tall_groups;
+                const int tap = p.tap_kblk[g * p.tall_taps_per_group + i];        // the packed K block of the group's i-th tap
                 const uint32_t aoff = static_cast<uint32_t>(i * p.tall_tap_bytes);      // a multiple of 1024: same swizzle phase
                 const uint64_t a_hi = umma_desc_k_sw128(sa + aoff);
                 const uint64_t a_lo = umma_desc_k_sw128(sa + plane_bytes + aoff);

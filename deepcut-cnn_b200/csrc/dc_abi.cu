@@ -620,10 +620,15 @@ int dc_conv_forward(const dc_conv_args* a, void* stream) {
   }
   p.H = h; p.W = w; p.Ho = out_h; p.Wo = out_w; p.Cout = a->cout; p.Cin = a->cin;
   p.ntaps = a->kh * a->kw;
+  // visiting order of the taps: row-major like the packed K axis, except for the 64 -> 64 channel 3x3 convs, which go column offset by
+  // column offset (ConvParams::tap_kblk: the order TALL mode needs, used by the plain kernel too so that both give the same bits)
+  const bool col_major_taps = a->kh == 3 && a->kw == 3 && a->cin == 64 && rows == 64;
   for (int pp = 0; pp < a->kh; ++pp)
     for (int q = 0; q < a->kw; ++q) {
-      p.tap_dy[pp * a->kw + q] = -a->pad + pp * a->dilation;
-      p.tap_dx[pp * a->kw + q] = -a->pad + q * a->dilation;
+      const int t = col_major_taps ? q * a->kh + pp : pp * a->kw + q;
+      p.tap_dy[t] = -a->pad + pp * a->dilation;
+      p.tap_dx[t] = -a->pad + q * a->dilation;
+      p.tap_kblk[t] = pp * a->kw + q;
     }
   // tile rectangle with the least padded area
   const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
@@ -764,7 +769,7 @@ int dc_conv1_tc_forward(const float* x, int n, int h, int w, const void* w_packe
   p.H = h2; p.W = w2; p.Ho = h2; p.Wo = w2; p.Cout = 64; p.Cin = 64;
   p.ntaps = 4;
   p.in_stride = 1;
-  for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t - 2; p.tap_dx[t] = 0; }
+  for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t - 2; p.tap_dx[t] = 0; p.tap_kblk[t] = t; }
   const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
   long long best = -1;
   for (int i = 0; i < 5; ++i) {

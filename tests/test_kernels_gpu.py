@@ -59,7 +59,7 @@ CONV_CASES = [
     # ragged in both directions, dilation 1 and 2, an odd tile count (phantom tile in the last pair)
     (64, 64, 3, 1, 1, 45, 83, 6),
     (64, 64, 3, 2, 2, 41, 70, 7),
-    (64, 48, 3, 1, 1, 60, 100, 3),
+    (64, 64, 3, 1, 1, 72, 100, 3),          # 7 x 9 x 3 = 189 tiles: odd
 ]
 
 
@@ -82,8 +82,9 @@ def test_conv_bn_relu_matches_oracle(case, _gpu):
 @pytest.mark.parametrize("case", [(1024, 256, 1, 0, 1, 45, 80, 6), (2048, 512, 1, 0, 1, 45, 83, 3), (256, 256, 3, 1, 1, 45, 80, 6), (512, 512, 3, 2, 2, 45, 80, 5),
                                   (64, 64, 3, 1, 1, 45, 83, 6), (64, 64, 3, 2, 2, 41, 70, 7)])
 def test_tile_and_pairing_choices_are_bitwise_neutral(case, _gpu, monkeypatch):
-    """dc_conv_forward's tile choices (CTA pairs or single CTAs for the 3x3 convs, 128- or 256-channel tiles; off-by-default forms
-    included) keep every output element's K chain: the same launch under each switch gives bitwise the same tensor."""
+    """dc_conv_forward's kernel choices (CTA pairs or single CTAs for the 3x3 convs, 128- or 256-channel tiles, TALL mode or one box
+    per tap for the 64 -> 64 channel convs; off-by-default forms included) keep every output element's K chain: the same launch under
+    each switch gives bitwise the same tensor."""
     ci, co, k, pad, dil, h, w, n = case
     rng = np.random.default_rng(ci + co + k)
     x = np.maximum(rng.standard_normal((n, ci, h, w)), 0).astype(np.float32)
