@@ -481,7 +481,7 @@ def main():
         rep = [s_ for s_ in info if s_[1].startswith("res5b_branch2b")]
         # `traffic` = DRAM bytes of that launch from the COMMITTED ncu launch list (profiles/r2_traffic.json: one profiled forward of this
         # workload, --cache-control none); it is not measured in this run -- `traffic_source` says so -- and only given for the workload it
-        # was captured on.  r1's --set full capture supplies the tensor-pipe reading.
+        # was captured on.
         tr_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if rep and rep[0][2] > 0:
             r_ach = rep[0][3] / (rep[0][2] / 1e3) / 1e12
@@ -495,8 +495,11 @@ def main():
                     roofline["traffic_source"] = "committed ncu capture, not measured in this run: profiles/r2_traffic.json (" + doc["source"].split(",")[0] + " ...)"
                     roofline["representative"]["traffic"] = tr["dram_bytes"]
                     roofline["forward_dram_bytes_ncu"] = doc.get("forward_dram_bytes")
+                # the --set full capture of that launch: this round's if the committed file has one, else round 1's (single-CTA form)
                 r1 = os.path.join(ROOT, "profiles", "r1_traffic.json")
-                if os.path.exists(r1):
+                if tr and "tensor_pipe_active_pct" in tr:
+                    roofline["representative"]["tensor_pipe_active_pct_ncu"] = tr["tensor_pipe_active_pct"]
+                elif os.path.exists(r1):
                     roofline["representative"]["tensor_pipe_active_pct_ncu"] = json.load(open(r1))["launches"]["res5b_branch2b"]["tensor_pipe_active_pct"]
         report = {"total_ms": total_ms, "steps": [{"type": s[0], "name": s[1], "ms": s[2], "gflop": s[3] / 1e9, "mbytes": s[4] / 1e6,
                                                     "tflops": (s[3] / (s[2] / 1e3) / 1e12) if s[2] > 0 else 0.0,
