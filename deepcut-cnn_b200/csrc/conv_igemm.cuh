@@ -19,7 +19,8 @@
 // Pipeline (persistent CTAs, static round-robin tile schedule):
 //   warp 0   TMA producer: 4 bulk-tensor loads / stage (A_hi, A_lo: 5-D NHWC boxes with
 //            negative/OOB coordinates zero-filled = padding & dilation; B_hi, B_lo)
-//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees stages
+//   warp 1   TMEM allocator + tcgen05.mma issuer; tcgen05.commit frees stages
+//            (both warps run their loops converged; one elect.sync lane issues -- see the producer)
 //   warps 2-9 epilogue (two per TMEM lane quarter): tcgen05.ld main + cross accumulators ->
 //            *scale[c] + shift[c] (+ residual) (ReLU) -> split fp16 NHWC stores; or fp32 rows for
 //            the head GEMMs, which run with A and B swapped (weights on the 128 accumulator
@@ -134,8 +135,9 @@ struct ConvCfg {
   // TMEM holds kAccBufs (main, cross) accumulator pairs of BN columns each: two for BN <= 128 (the epilogue of tile i overlaps the
   // MMAs of tile i+1), ONE for BN = 256 (all 512 columns).  BN = 256 exists for the long-K 1x1 reduce convs: one A tile against 256
   // channels (64 KB per 2 x 768 MMA cycles instead of 48 KB per 768, half as many MMA issues per FLOP) measured ~7 % faster per unit
-  // of work than two 128-channel tiles despite the un-overlapped epilogue -- and only pays where halving the unit count does not
-  // cost a wave (dc_conv_forward decides; profiles/r2_ncu_summary.md).
+  // of work than two 128-channel tiles while every MMA issue cost a ~14-instruction waterfall; with the elect.sync issue path the
+  // 128-channel pairs are faster everywhere it had been chosen, so dc_conv_forward no longer takes it unless DC_CONV_BN256 asks
+  // (profiles/r2_round2_sweeps.md).  Kept: it is bitwise-neutral, tested, and the tile a longer-K layer would want.
   static constexpr int kAccBufs = BN == 256 ? 1 : 2;
   static_assert(EW == 8 || (EW == 16 && BN == 128), "the 16-warp epilogue owns one 32-channel chunk per warp: BN = 128");
   static constexpr int kStages = BN == 256 ? 3 : (CG == 2 ? 4 : (BN >= 128 ? 3 : 4)) - (EW == 16 ? 1 : 0);
