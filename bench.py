@@ -555,7 +555,10 @@ def main():
                            "l2_policy": "inputs larger than L2 (per-step activations >> 126 MB)", "outputs": "prob, loc_pred, next_pred"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred", "mode": e2e_mode},
+                        "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred", "mode": e2e_mode,
+                        # what the requests in flight cost in device memory: every Net has its own arena and its own packed weights
+                        "nets_per_rank": (args.e2e_inflight if (args.e2e_inflight > 1 and not exchange) else 1),
+                        "device_mib_per_net": {"arena": net.arena_bytes >> 20, "packed_weights": net.weight_bytes >> 20}},
                 "exchange": exchange_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency, "without_next_pred": subset,
                 "wall_ms_per_step": wall_ms / args.steps, "arena_mib": net.arena_bytes >> 20, "weights_mib": net.weight_bytes >> 20}
         emit(line)
