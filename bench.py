@@ -342,6 +342,7 @@ def main():
     launches = L.dc_launch_count() - launches0
     clocks = sampler.stop(*timed.window) if rank == 0 else None
     value = world * B * args.steps / (dev_ms / 1e3)
+    arena_mib, weights_mib = net.arena_bytes >> 20, net.weight_bytes >> 20      # of the plan just timed (later sections re-plan)
 
     # ---- end to end through the Caffe API with host buffers
     prob, loc = net.blobs["prob"], net.blobs["loc_pred"]
@@ -558,9 +559,9 @@ def main():
                         "ms_per_step": e2e_wall_ms / args.steps, "reads": "prob, loc_pred", "mode": e2e_mode,
                         # what the requests in flight cost in device memory: every Net has its own arena and its own packed weights
                         "nets_per_rank": (args.e2e_inflight if (args.e2e_inflight > 1 and not exchange) else 1),
-                        "device_mib_per_net": {"arena": net.arena_bytes >> 20, "packed_weights": net.weight_bytes >> 20}},
+                        "device_mib_per_net": {"arena": arena_mib, "packed_weights": weights_mib}},
                 "exchange": exchange_rec, "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_config": latency, "without_next_pred": subset,
-                "wall_ms_per_step": wall_ms / args.steps, "arena_mib": net.arena_bytes >> 20, "weights_mib": net.weight_bytes >> 20}
+                "wall_ms_per_step": wall_ms / args.steps, "arena_mib": arena_mib, "weights_mib": weights_mib}
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
